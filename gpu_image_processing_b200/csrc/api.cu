@@ -1,0 +1,372 @@
+// api.cu -- the C ABI (include/gip_b200.h) and the reference's C++ entry points
+// (include/image_filters.h) on top of the kernels.  Validation, job construction, dispatch
+// between the fused fast path and the general path, CUDA-event timing, host-buffer staging.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/gip_b200.h"
+#include "../../include/image_filters.h"
+#include "common.cuh"
+
+namespace gip {
+
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_path{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static bool verbose() {
+    static const bool v = [] { const char* e = getenv("GIP_VERBOSE"); return e && e[0] == '1'; }();
+    return v;
+}
+
+// image_filters.cu:25-39 -- float32 expf, running float32 sum, divide.  Host libm, like the reference.
+static void gaussian_weights_host(float* k, int radius, float sigma) {
+    float sum = 0.0f;
+    for (int i = -radius; i <= radius; i++) {
+        const float x = static_cast<float>(i);
+        const float v = expf(-(x * x) / (2.0f * sigma * sigma));
+        k[radius + i] = v;
+        sum += v;
+    }
+    for (int i = 0; i < 2 * radius + 1; i++) k[i] /= sum;
+}
+
+static int level_ok(FilterKind kind, int level) {
+    if (kind == kGaussian) return level == GIP_LEVEL_NAIVE || level == GIP_LEVEL_TEXTURE_MEMORY;
+    return level == GIP_LEVEL_NAIVE || level == GIP_LEVEL_SHARED_MEMORY;
+}
+
+struct BandArgs {
+    const uint8_t* above = nullptr;
+    const uint8_t* below = nullptr;
+    int64_t y0 = 0, rows = -1, rows_above = 0, rows_below = 0;
+};
+
+// Validate and enqueue one filter.  All entry points funnel through here.
+static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out, int64_t width,
+                           int64_t height, int channels, int64_t batch, float sigma, int radius,
+                           int level, const BandArgs* band, cudaStream_t stream) {
+    if (!level_ok(kind, level)) {
+        if (verbose()) fprintf(stderr, "gip: level %d is not implemented for this filter\n", level);
+        return cudaErrorNotSupported;   // image_filters.cu:693-696, :958-961, :1615-1618
+    }
+    if (!d_in || !d_out || width <= 0 || height <= 0 || batch <= 0) return cudaErrorInvalidValue;
+    if (channels != 1 && channels != 3 && channels != 4) return cudaErrorInvalidValue;
+    if (kind != kSobel && radius < 0) return cudaErrorInvalidValue;
+    if (kind == kGaussian && !(sigma > 0.0f)) return cudaErrorInvalidValue;
+    if (kind == kSobel) radius = 1;
+
+    Job job;
+    memset(&job, 0, sizeof(job));
+    job.width = width; job.height = height; job.channels = channels; job.batch = batch;
+    job.radius = radius;
+    job.sobel_u8_gray = (kind == kSobel && level == GIP_LEVEL_SHARED_MEMORY) ? 1 : 0;
+    job.out = d_out;
+    job.src.pitch = width * channels;
+    job.src.image_stride = job.src.pitch * height;
+    job.src.band = d_in;
+    job.src.band_y0 = 0; job.src.band_y1 = height; job.src.above_y0 = 0;
+    if (band) {
+        if (batch != 1 || band->y0 < 0 || band->rows <= 0 || band->y0 + band->rows > height)
+            return cudaErrorInvalidValue;
+        const int64_t y1 = band->y0 + band->rows;
+        const int64_t need_above = band->y0 < radius ? band->y0 : radius;
+        const int64_t need_below = (height - y1) < radius ? (height - y1) : radius;
+        if (band->rows_above < need_above || (need_above > 0 && !band->above)) return cudaErrorInvalidValue;
+        if (band->rows_below < need_below || (need_below > 0 && !band->below)) return cudaErrorInvalidValue;
+        job.src.band_y0 = band->y0; job.src.band_y1 = y1;
+        job.src.above = band->above; job.src.above_y0 = band->y0 - band->rows_above;
+        job.src.below = band->below;
+    }
+
+    float* d_wide = nullptr;
+    cudaError_t err = cudaSuccess;
+    if (kind == kGaussian) {
+        if (radius <= kMaxFusedRadius) {
+            gaussian_weights_host(job.weights, radius, sigma);
+        } else {
+            const size_t n = 2 * (size_t)radius + 1;
+            float* h = (float*)malloc(n * sizeof(float));
+            if (!h) return cudaErrorMemoryAllocation;
+            gaussian_weights_host(h, radius, sigma);
+            err = cudaMallocAsync((void**)&d_wide, n * sizeof(float), stream);
+            if (err == cudaSuccess)   // pageable source: staged before the call returns
+                err = cudaMemcpyAsync(d_wide, h, n * sizeof(float), cudaMemcpyHostToDevice, stream);
+            free(h);
+            if (err != cudaSuccess) { if (d_wide) cudaFreeAsync(d_wide, stream); return err; }
+        }
+    }
+
+    bool handled = false;
+    if (g_path.load() == 0 && radius <= kMaxFusedRadius) err = launch_fast(kind, job, stream, &handled);
+    if (!handled && err == cudaSuccess) err = launch_general(kind, job, d_wide, stream);
+    if (d_wide) cudaFreeAsync(d_wide, stream);
+    return err;
+}
+
+static void fill_metrics(gip_metrics* m, float ms, FilterKind kind, int64_t bytes) {
+    if (!m) return;
+    // reference convention: blurs count 4x the image (two passes, :905-906, :1094-1095), Sobel 2x (:1711-1712)
+    const double moved = (double)bytes * (kind == kSobel ? 2.0 : 4.0);
+    m->time_ms = ms;
+    m->bandwidth_gbps = ms > 0.0f ? (float)(moved / (ms / 1000.0) / (1024.0 * 1024.0 * 1024.0)) : 0.0f;
+    m->fps = ms > 0.0f ? 1000.0f / ms : 0.0f;
+}
+
+// Synchronous device-pointer call on the legacy default stream, timed with events like the reference.
+static cudaError_t run_sync(FilterKind kind, const uint8_t* d_in, uint8_t* d_out, int width, int height,
+                            int channels, float sigma, int radius, int level, gip_metrics* metrics) {
+    if (!level_ok(kind, level)) {           // before anything touches the device, like the reference
+        if (verbose()) fprintf(stderr, "gip: level %d is not implemented for this filter\n", level);
+        return cudaErrorNotSupported;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaEventCreate(&e0);
+    if (err != cudaSuccess) return err;
+    err = cudaEventCreate(&e1);
+    if (err != cudaSuccess) { cudaEventDestroy(e0); return err; }
+    cudaEventRecord(e0, 0);
+    err = enqueue(kind, d_in, d_out, width, height, channels, 1, sigma, radius, level, nullptr, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t serr = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (err == cudaSuccess && serr == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) return err;
+    if (serr != cudaSuccess) return serr;
+    fill_metrics(metrics, ms, kind, (int64_t)width * height * channels);
+    if (verbose()) printf("gip: %s %dx%dx%d r=%d level=%d: %.3f ms\n",
+                          kind == kGaussian ? "gaussian" : kind == kBox ? "box" : "sobel",
+                          width, height, channels, radius, level, ms);
+    return cudaSuccess;
+}
+
+// ---- host-buffer path: cached pinned + device staging ---------------------------------------
+struct HostCache {
+    std::mutex mu;
+    int device = -1;
+    uint8_t *d_in = nullptr, *d_out = nullptr, *p_in = nullptr, *p_out = nullptr;
+    size_t d_cap = 0, p_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+
+    void release() {
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+        if (p_in) cudaFreeHost(p_in);
+        if (p_out) cudaFreeHost(p_out);
+        d_in = d_out = p_in = p_out = nullptr; d_cap = p_cap = 0;
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        if (e0) { cudaEventDestroy(e0); e0 = nullptr; }
+        if (e1) { cudaEventDestroy(e1); e1 = nullptr; }
+        device = -1;
+    }
+    cudaError_t ensure(size_t bytes, bool need_pinned) {
+        int dev = 0;
+        cudaError_t err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) return err;
+        if (dev != device) { release(); device = dev; }
+        if (!stream) {
+            if ((err = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return err;
+            if ((err = cudaEventCreate(&e0)) != cudaSuccess) return err;
+            if ((err = cudaEventCreate(&e1)) != cudaSuccess) return err;
+        }
+        if (bytes > d_cap) {
+            if (d_in) cudaFree(d_in);
+            if (d_out) cudaFree(d_out);
+            d_in = d_out = nullptr; d_cap = 0;
+            if ((err = cudaMalloc((void**)&d_in, bytes)) != cudaSuccess) return err;
+            if ((err = cudaMalloc((void**)&d_out, bytes)) != cudaSuccess) return err;
+            d_cap = bytes;
+        }
+        if (need_pinned && bytes > p_cap) {
+            if (p_in) cudaFreeHost(p_in);
+            if (p_out) cudaFreeHost(p_out);
+            p_in = p_out = nullptr; p_cap = 0;
+            if ((err = cudaMallocHost((void**)&p_in, bytes)) != cudaSuccess) return err;
+            if ((err = cudaMallocHost((void**)&p_out, bytes)) != cudaSuccess) return err;
+            p_cap = bytes;
+        }
+        return cudaSuccess;
+    }
+};
+static HostCache g_cache;
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// bindings.cpp:37-42, :57-63, :77-81 -- H2D, filter, D2H; here with cached buffers, pinned
+// staging (skipped when the caller's memory is already pinned) and a private stream.
+static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out, int64_t width,
+                            int64_t height, int channels, int64_t batch, float sigma, int radius,
+                            int level, gip_metrics* metrics) {
+    if (!level_ok(kind, level)) return cudaErrorNotSupported;
+    if (!h_in || !h_out || width <= 0 || height <= 0 || batch <= 0) return cudaErrorInvalidValue;
+    if (channels != 1 && channels != 3 && channels != 4) return cudaErrorInvalidValue;
+    const size_t bytes = (size_t)width * height * channels * batch;
+    std::lock_guard<std::mutex> lock(g_cache.mu);
+    const bool pin_in = is_pinned(h_in), pin_out = is_pinned(h_out);
+    cudaError_t err = g_cache.ensure(bytes, !(pin_in && pin_out));
+    if (err != cudaSuccess) return err;
+    cudaStream_t s = g_cache.stream;
+    const uint8_t* src = h_in;
+    if (!pin_in) { memcpy(g_cache.p_in, h_in, bytes); src = g_cache.p_in; }
+    uint8_t* dst = pin_out ? h_out : g_cache.p_out;
+    if ((err = cudaMemcpyAsync(g_cache.d_in, src, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return err;
+    cudaEventRecord(g_cache.e0, s);
+    err = enqueue(kind, g_cache.d_in, g_cache.d_out, width, height, channels, batch, sigma, radius, level, nullptr, s);
+    cudaEventRecord(g_cache.e1, s);
+    if (err != cudaSuccess) { cudaStreamSynchronize(s); return err; }
+    if ((err = cudaMemcpyAsync(dst, g_cache.d_out, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return err;
+    if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return err;
+    if (!pin_out) memcpy(h_out, g_cache.p_out, bytes);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, g_cache.e0, g_cache.e1);
+    fill_metrics(metrics, ms, kind, (int64_t)bytes);
+    return cudaSuccess;
+}
+
+}  // namespace gip
+
+using namespace gip;
+
+// ============================== extern "C" ABI ===============================================
+extern "C" {
+
+int gip_gaussian_blur(const uint8_t* d_input, uint8_t* d_output, int width, int height, int channels,
+                      float sigma, int radius, int level, gip_metrics* metrics) {
+    return (int)run_sync(kGaussian, d_input, d_output, width, height, channels, sigma, radius, level, metrics);
+}
+int gip_box_blur(const uint8_t* d_input, uint8_t* d_output, int width, int height, int channels,
+                 int radius, int level, gip_metrics* metrics) {
+    return (int)run_sync(kBox, d_input, d_output, width, height, channels, 0.0f, radius, level, metrics);
+}
+int gip_sobel(const uint8_t* d_input, uint8_t* d_output, int width, int height, int channels,
+              int level, gip_metrics* metrics) {
+    return (int)run_sync(kSobel, d_input, d_output, width, height, channels, 0.0f, 1, level, metrics);
+}
+
+int gip_gaussian_blur_async(const uint8_t* d_input, uint8_t* d_output, int64_t width, int64_t height,
+                            int channels, int64_t batch, float sigma, int radius, int level, void* stream) {
+    return (int)enqueue(kGaussian, d_input, d_output, width, height, channels, batch, sigma, radius, level,
+                        nullptr, (cudaStream_t)stream);
+}
+int gip_box_blur_async(const uint8_t* d_input, uint8_t* d_output, int64_t width, int64_t height,
+                       int channels, int64_t batch, int radius, int level, void* stream) {
+    return (int)enqueue(kBox, d_input, d_output, width, height, channels, batch, 0.0f, radius, level,
+                        nullptr, (cudaStream_t)stream);
+}
+int gip_sobel_async(const uint8_t* d_input, uint8_t* d_output, int64_t width, int64_t height,
+                    int channels, int64_t batch, int level, void* stream) {
+    return (int)enqueue(kSobel, d_input, d_output, width, height, channels, batch, 0.0f, 1, level,
+                        nullptr, (cudaStream_t)stream);
+}
+
+static BandArgs band_args(const uint8_t* above, const uint8_t* below, int64_t y0, int64_t rows,
+                          int64_t ra, int64_t rb) {
+    BandArgs b; b.above = above; b.below = below; b.y0 = y0; b.rows = rows; b.rows_above = ra; b.rows_below = rb;
+    return b;
+}
+int gip_gaussian_blur_band(const uint8_t* d_band, const uint8_t* d_above, const uint8_t* d_below,
+                           uint8_t* d_output, int64_t width, int64_t height, int channels,
+                           int64_t band_y0, int64_t band_rows, int64_t rows_above, int64_t rows_below,
+                           float sigma, int radius, int level, void* stream) {
+    BandArgs b = band_args(d_above, d_below, band_y0, band_rows, rows_above, rows_below);
+    return (int)enqueue(kGaussian, d_band, d_output, width, height, channels, 1, sigma, radius, level, &b,
+                        (cudaStream_t)stream);
+}
+int gip_box_blur_band(const uint8_t* d_band, const uint8_t* d_above, const uint8_t* d_below,
+                      uint8_t* d_output, int64_t width, int64_t height, int channels,
+                      int64_t band_y0, int64_t band_rows, int64_t rows_above, int64_t rows_below,
+                      int radius, int level, void* stream) {
+    BandArgs b = band_args(d_above, d_below, band_y0, band_rows, rows_above, rows_below);
+    return (int)enqueue(kBox, d_band, d_output, width, height, channels, 1, 0.0f, radius, level, &b,
+                        (cudaStream_t)stream);
+}
+int gip_sobel_band(const uint8_t* d_band, const uint8_t* d_above, const uint8_t* d_below,
+                   uint8_t* d_output, int64_t width, int64_t height, int channels,
+                   int64_t band_y0, int64_t band_rows, int64_t rows_above, int64_t rows_below,
+                   int level, void* stream) {
+    BandArgs b = band_args(d_above, d_below, band_y0, band_rows, rows_above, rows_below);
+    return (int)enqueue(kSobel, d_band, d_output, width, height, channels, 1, 0.0f, 1, level, &b,
+                        (cudaStream_t)stream);
+}
+
+int gip_gaussian_blur_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int64_t height,
+                           int channels, int64_t batch, float sigma, int radius, int level,
+                           gip_metrics* metrics) {
+    return (int)run_host(kGaussian, h_input, h_output, width, height, channels, batch, sigma, radius, level, metrics);
+}
+int gip_box_blur_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int64_t height,
+                      int channels, int64_t batch, int radius, int level, gip_metrics* metrics) {
+    return (int)run_host(kBox, h_input, h_output, width, height, channels, batch, 0.0f, radius, level, metrics);
+}
+int gip_sobel_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int64_t height,
+                   int channels, int64_t batch, int level, gip_metrics* metrics) {
+    return (int)run_host(kSobel, h_input, h_output, width, height, channels, batch, 0.0f, 1, level, metrics);
+}
+
+int gip_ipc_export(const void* d_ptr, uint8_t handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_ptr || !handle_out) return (int)cudaErrorInvalidValue;
+    cudaIpcMemHandle_t h;
+    cudaError_t err = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
+    if (err == cudaSuccess) memcpy(handle_out, &h, 64);
+    return (int)err;
+}
+int gip_ipc_open(const uint8_t handle[64], void** d_ptr_out) {
+    if (!handle || !d_ptr_out) return (int)cudaErrorInvalidValue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return (int)cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int gip_ipc_close(void* d_ptr) { return (int)cudaIpcCloseMemHandle(d_ptr); }
+int gip_enable_peer_access(int peer_device) {
+    cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); err = cudaSuccess; }
+    return (int)err;
+}
+
+int gip_gaussian_weights(float* weights_out, int radius, float sigma) {
+    if (!weights_out || radius < 0 || !(sigma > 0.0f)) return (int)cudaErrorInvalidValue;
+    gaussian_weights_host(weights_out, radius, sigma);
+    return 0;
+}
+const char* gip_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+int64_t gip_launch_count(void) { return g_launches.load(); }
+int gip_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_cache.mu);
+    g_cache.release();
+    return 0;
+}
+const char* gip_version(void) { return "gip_b200 0.1 sm_100a"; }
+int gip_set_path(int path) { return g_path.exchange(path); }
+
+}  // extern "C"
+
+// ============================== reference C++ entry points ====================================
+// Same mangled names as cuda_lib/include/image_filters.h:46-112.
+cudaError_t gaussianBlur(unsigned char* d_input, unsigned char* d_output, int width, int height,
+                         int channels, float sigma, int kernelRadius, OptimizationLevel level,
+                         PerformanceMetrics* metrics) {
+    static_assert(sizeof(PerformanceMetrics) == sizeof(gip_metrics), "metrics layout");
+    return run_sync(kGaussian, d_input, d_output, width, height, channels, sigma, kernelRadius, (int)level,
+                    reinterpret_cast<gip_metrics*>(metrics));
+}
+cudaError_t boxBlur(unsigned char* d_input, unsigned char* d_output, int width, int height,
+                    int channels, int kernelRadius, OptimizationLevel level, PerformanceMetrics* metrics) {
+    return run_sync(kBox, d_input, d_output, width, height, channels, 0.0f, kernelRadius, (int)level,
+                    reinterpret_cast<gip_metrics*>(metrics));
+}
+cudaError_t sobelEdgeDetection(unsigned char* d_input, unsigned char* d_output, int width, int height,
+                               int channels, OptimizationLevel level, PerformanceMetrics* metrics) {
+    return run_sync(kSobel, d_input, d_output, width, height, channels, 0.0f, 1, (int)level,
+                    reinterpret_cast<gip_metrics*>(metrics));
+}

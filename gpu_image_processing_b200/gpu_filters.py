@@ -1,0 +1,90 @@
+"""`gpu_filters` -- the Python module of the reference (backend/cuda_bindings/bindings.cpp:240-283)
+re-hosted on libgip_b200.so through the C ABI.
+
+Same functions, keyword names, defaults, return dict and error text:
+    gaussian_blur(image, sigma=2.0, radius=3, level=1)      bindings.cpp:12-91, :243-254
+    box_blur(image, radius=3, level=1)                      bindings.cpp:96-163, :256-266
+    sobel_edge_detection(image, level=1)                    bindings.cpp:168-237, :268-277
+    NAIVE=1, SHARED_MEMORY=2, TEXTURE_MEMORY=3              bindings.cpp:280-282
+`image` is a numpy (H, W, C) array, C in {1,3,4}; any dtype is cast to uint8 the way
+py::array_t<unsigned char> does.  Returns {"image": uint8 (H,W,C), "time_ms", "bandwidth_gbps",
+"fps"}.  Errors are RuntimeError with the reference's messages.
+
+Differences: the array is made C-contiguous first (the reference reads a strided buffer as if
+it were dense); device and pinned buffers are cached between calls instead of cudaMalloc/cudaFree
+per call (bindings.cpp:37-39, :80-81); the GIL is released while the GPU works (ctypes).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+NAIVE = 1
+SHARED_MEMORY = 2
+TEXTURE_MEMORY = 3
+
+
+def _prepare(image):
+    a = np.asarray(image)
+    if a.ndim != 3:
+        raise RuntimeError("Input must be 3D array (height, width, channels)")
+    if a.dtype != np.uint8:
+        a = a.astype(np.uint8)          # py::array_t<unsigned char> forcecast
+    a = np.ascontiguousarray(a)
+    h, w, c = a.shape
+    if c not in (1, 3, 4):
+        raise RuntimeError("Channels must be 1, 3, or 4")
+    if h == 0 or w == 0:
+        raise RuntimeError("CUDA error: invalid argument")
+    return a, np.empty_like(a), h, w, c
+
+
+def _result(out, m):
+    return {"image": out, "time_ms": float(m.time_ms), "bandwidth_gbps": float(m.bandwidth_gbps),
+            "fps": float(m.fps)}
+
+
+def _run(fn, *args):
+    code = fn(*args)
+    if code != 0:
+        raise RuntimeError(str(_lib.CudaError(code)))
+
+
+def gaussian_blur(image, sigma: float = 2.0, radius: int = 3, level: int = 1):
+    """Apply Gaussian blur to image using GPU (level 1=naive, 2=texture_memory)."""
+    a, out, h, w, c = _prepare(image)
+    if level == 1:
+        lvl = NAIVE
+    elif level == 2:
+        lvl = TEXTURE_MEMORY                      # bindings.cpp:48
+    else:
+        raise RuntimeError("Level must be 1 (naive) or 2 (texture_memory) for Gaussian blur")
+    m = _lib.Metrics()
+    _run(_lib.load().gip_gaussian_blur_host, a.ctypes.data, out.ctypes.data, w, h, c, 1,
+         float(sigma), int(radius), lvl, ctypes.byref(m))
+    return _result(out, m)
+
+
+def box_blur(image, radius: int = 3, level: int = 1):
+    """Apply Box blur to image using GPU (level 1=naive, 2=shared_memory)."""
+    a, out, h, w, c = _prepare(image)
+    if level not in (1, 2):
+        raise RuntimeError("Level must be 1 (naive) or 2 (shared_memory)")
+    m = _lib.Metrics()
+    _run(_lib.load().gip_box_blur_host, a.ctypes.data, out.ctypes.data, w, h, c, 1, int(radius),
+         int(level), ctypes.byref(m))
+    return _result(out, m)
+
+
+def sobel_edge_detection(image, level: int = 1):
+    """Apply Sobel edge detection to image using GPU (level 1=naive, 2=shared_memory)."""
+    a, out, h, w, c = _prepare(image)
+    if level not in (1, 2):
+        raise RuntimeError("Level must be 1 (naive) or 2 (shared_memory) for Sobel edge detection")
+    m = _lib.Metrics()
+    _run(_lib.load().gip_sobel_host, a.ctypes.data, out.ctypes.data, w, h, c, 1, int(level),
+         ctypes.byref(m))
+    return _result(out, m)
