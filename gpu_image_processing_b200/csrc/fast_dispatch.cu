@@ -9,7 +9,7 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
 
 cudaError_t launch_fast(FilterKind kind, const Job& job, cudaStream_t stream, bool* handled) {
     *handled = false;
-    (void)kind; (void)job; (void)stream;
+    if (kind == kBox) return launch_fast_box(job, stream, handled);
     return cudaSuccess;
 }
 
