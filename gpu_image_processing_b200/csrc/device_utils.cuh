@@ -62,6 +62,34 @@ __device__ __forceinline__ float fma_rz(float a, float b, float c) {
     return d;
 }
 
+// packed float pairs (FFMA2 / FADD2): two lanes per issue slot
+__device__ __forceinline__ uint64_t pack_f2(uint32_t lo, uint32_t hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_rz_x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_rn_x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void stg64_stream(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // bytes [k, k+4) of the 8-byte little-endian pair (lo, hi), k = shift_bits/8 in 0..3
 __device__ __forceinline__ uint32_t funnel_bytes(uint32_t lo, uint32_t hi, uint32_t shift_bits) {
     return __funnelshift_r(lo, hi, shift_bits);
