@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the filter hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): box blur, radius sweep 1..31, on a synthetic 4096x4096 RGBA u8
+image.  One *step* = the whole sweep = 31 launches of the fused kernel (one per radius).  Launch i
+works on image pair i mod 4, four distinct 64 MiB input / output pairs per GPU (512 MiB > the 126 MB
+L2), so every launch streams from HBM.  With N > 1 every rank runs the same sweep on its own images
+(image batches shard per GPU, no data-path collective): weak scaling, value = all ranks' pixels / the
+slowest rank's time.
+
+The JSON line carries
+  value      Mpix/s, device-resident, CUDA events on the launch stream, max over ranks
+  e2e        the same sweep through the reference-facing call gip_box_blur_host (what gpu_filters.box_blur
+             does) from pinned host memory: H2D + kernel + D2H inside the timed region
+  roofline   dominant kernel gip_box_fused: algorithmic bytes (2 bytes per image byte) / launch time
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (straight C transcription of the reference's level-1 math, OpenMP over all
+             host cores) on a bounded sample of the same sweep; N = 1 only
+  filters    device-resident Mpix/s and GB/s of the other BASELINE configs (c1 Gaussian, c3 Sobel), N = 1 only
+`--impl reference` times the CPU port (the reference has no CPU implementation of this path; its own
+implementation is CUDA and is reported in `reference_cuda_same_gpu` of the main line).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, C = 4096, 4096, 4
+RADII = list(range(1, 32))
+NBUF = 4
+METRIC = "Mpix/s, box blur radius sweep 1..31 on 4096x4096 RGBA u8 (aggregate over GPUs)"
+CONFIG = {"workload": "c2: box blur radius sweep r=1..31, 4096x4096 RGBA u8, one image per launch, "
+                      "4 rotating 64 MiB image pairs per GPU (working set 512 MiB > L2)",
+          "step": "31 launches (one per radius)", "l2_policy": "inputs larger than L2 (rotating buffers)",
+          "sharding": "independent image batches per GPU, no collective"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_run(steps, warmup, rows=1024):
+    """The oracle on all host threads over a bounded sample: the full radius sweep on a 4096 x `rows` RGBA band."""
+    from oracle import oracle as O
+    from tests import synth
+    img = synth.uniform(rows, W, C, seed=1234)
+    cores = O.max_threads()
+    for _ in range(max(0, min(warmup, 1))):
+        O.box_blur(img, 3)
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        for r in RADII:
+            O.box_blur(img, r)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    mpix = rows * W * len(RADII) / best / 1e6
+    return {"value": mpix, "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"full radius sweep r=1..31 on a {W}x{rows} RGBA band (1/{H // rows} of the image), "
+                      f"best of {len(times)}, {best:.2f} s per sweep; straight C transcription of the reference's "
+                      "level-1 math (oracle/filters_oracle.c), OpenMP over all host threads"}, best
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU port on the host cores (the reference itself has no CPU path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 3))
+    base, sweep_s = cpu_port_run(steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sweep_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference arm = CPU port of the reference's level-1 math on the host cores; each step is the "
+                    "bounded sample named in cpu_baseline.sample"}
+    print(json.dumps(line))
+    return 0
+
+
+def reference_cuda_same_gpu(torch, x, y):
+    """the reference's own kernels (oracle/_ref, unmodified, sm_100a) on this GPU, same sweep.
+    Level 2 (shared memory) for r <= 16, level 1 above (its level 2 is wrong for r > 16)."""
+    try:
+        from oracle import oracle as O
+        if not O.ref_available():
+            return {"unavailable": "oracle/_ref not built"}
+        total_ms, n = 0.0, 0
+        for r in RADII:
+            lvl = 2 if r <= 16 else 1
+            rc, ms = O.ref_call("box", x.data_ptr(), y.data_ptr(), W, H, C, lvl, 0.0, r)
+            if rc != 0:
+                return {"unavailable": f"reference returned {rc} at r={r}"}
+            total_ms += ms
+            n += 1
+        torch.cuda.synchronize()
+        return {"value": H * W * n / (total_ms / 1e3) / 1e6, "unit": "Mpix/s", "ms_per_sweep": total_ms,
+                "how": "reference boxBlur() time_ms (its own CUDA events, kernels only), level 2 for r<=16, level 1 for r>16"}
+    except Exception as e:  # the baseline must never take the bench down
+        return {"unavailable": repr(e)}
+
+
+def other_configs(torch, device_mod):
+    """Device-resident timings of BASELINE configs c1 (Gaussian) and c3 (Sobel): reported, not the headline."""
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def timed(fn, nbytes, npix, reps=12):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        return {"us": ms * 1e3, "Mpix/s": npix / ms / 1e3, "alg_GB/s": 2 * nbytes / ms / 1e6}
+
+    for name, (h, w, c), nb, call in (
+            ("c1_gaussian_3239x2146_rgb_s2_r3", (2146, 3239, 3), 8, lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 2, out=y)),
+            ("c3_sobel_7680x4320_rgb", (4320, 7680, 3), 3, lambda x, y: device_mod.sobel_edge_detection(x, 1, out=y)),
+            ("box_r3_1920x1080_rgb_x64", (64 * 1080, 1920, 3), 2, None)):
+        try:
+            if call is None:
+                xs = [torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
+                ys = [torch.empty_like(t) for t in xs]
+                out[name] = timed(lambda i: device_mod.box_blur(xs[i % nb], 3, 2, out=ys[i % nb]), xs[0].numel(), 64 * 1080 * 1920)
+            else:
+                xs = [torch.randint(0, 256, (h, w, c), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
+                ys = [torch.empty_like(t) for t in xs]
+                out[name] = timed(lambda i: call(xs[i % nb], ys[i % nb]), h * w * c, h * w)
+            del xs, ys
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / other configs / reference kernels")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from gpu_image_processing_b200 import _lib, device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.load()
+    warmup = max(3, args.warmup)
+
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    xs = [torch.randint(0, 256, (H, W, C), dtype=torch.uint8, device="cuda", generator=g) for _ in range(NBUF)]
+    ys = [torch.empty_like(x) for x in xs]
+    stream = torch.cuda.current_stream()
+
+    def step(k):
+        for i, r in enumerate(RADII):
+            b = (k * len(RADII) + i) % NBUF
+            device.box_blur(xs[b], r, 2, out=ys[b])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for k in range(warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.gip_launch_count()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.gip_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * H * W * len(RADII) / (ms_per_step / 1e3) / 1e6
+
+    # ---- end to end through the host-buffer entry point (what gpu_filters.box_blur calls), pinned host memory
+    e2e_steps = max(1, min(args.steps, 3))
+    hx = torch.randint(0, 256, (H, W, C), dtype=torch.uint8).pin_memory()
+    hy = torch.empty_like(hx).pin_memory()
+    m = _lib.Metrics()
+
+    def e2e_step():
+        for r in RADII:
+            _lib.check(L.gip_box_blur_host(hx.data_ptr(), hy.data_ptr(), W, H, C, 1, r, 2, ctypes.byref(m)))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * H * W * len(RADII) * e2e_steps / e2e_s / 1e6
+    img_bytes = H * W * C
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        us_per_launch = ms_per_step * 1e3 / len(RADII)
+        achieved = 2 * img_bytes / (us_per_launch * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": CONFIG,
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": img_bytes * len(RADII),
+                    "d2h_bytes_per_step": img_bytes * len(RADII), "steps": e2e_steps,
+                    "api": "gip_box_blur_host (C ABI behind gpu_filters.box_blur), pinned host buffers, per-call H2D + kernel + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gip_box_fused<4,true>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2 * img_bytes, "us_per_launch": us_per_launch,
+                         "frac_of_8TBs_nominal": achieved / 8000.0},
+        }
+        if world == 1 and not args.no_extras:
+            line["cpu_baseline"], _ = cpu_port_run(1, 1)
+            line["reference_cuda_same_gpu"] = reference_cuda_same_gpu(torch, xs[0], ys[0])
+            line["filters"] = other_configs(torch, device)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

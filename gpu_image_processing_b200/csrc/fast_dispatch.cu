@@ -10,6 +10,7 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
 cudaError_t launch_fast(FilterKind kind, const Job& job, cudaStream_t stream, bool* handled) {
     *handled = false;
     if (kind == kBox) return launch_fast_box(job, stream, handled);
+    if (kind == kSobel) return launch_fast_sobel(job, stream, handled);
     return cudaSuccess;
 }
 

@@ -1,0 +1,283 @@
+// fast_sobel.cu -- fused grayscale + 3x3 Sobel + magnitude for sm_100a, one pass, registers only.
+//
+// Replaces sobelEdgeDetectionNaive / sobelEdgeDetectionShared
+// (/root/reference/cuda_lib/src/image_filters.cu:1152-1315, :1329-1597): the reference reads 27 bytes
+// and converts 9 pixels to gray for every output pixel; here every input byte is read once and every
+// gray value is computed once.
+//
+// A warp owns a strip of 120 output pixels and marches down a band of rows.  Lane l holds 4 consecutive
+// pixels (12 / 16 / 4 bytes for RGB / RGBA / gray, loaded as 32-bit words: 384 contiguous bytes per warp
+// row); lanes 0 and 31 are halo lanes whose pixels are only read by their neighbours.  The gray values of
+// the previous two rows stay in registers; x+-1 neighbours come from __shfl_up/down.  No shared memory, no
+// block barrier.  Arithmetic is packed float32x2 (FADD2/FMUL2/FFMA2: pixels 0,2 and 1,3 of a lane form
+// the pairs) and reproduces the reference's rounding sequence exactly:
+//   u8 -> float     PRMT into the mantissa of 2^23, minus 2^23 (exact)
+//   gray            fma(B, .114f, fma(R, .299f, G * .587f))            (:1245, order read off the reference SASS)
+//   level 2         gray := (float)(uchar)(gray + 0.5f)                  (:1443-1444)
+//   gx, gy          single-rounded adds in row-major tap order          (:1246-1299)
+//   magnitude       fma(gx, gx, gy*gy); sqrtf as the reference's inlined sequence
+//                   (MUFU.RSQ, x*r, r/2, fma(-s,s,x), fma(d,h,s)); fminf(., 255); +0.5f; truncate (:1303-1305)
+//   borders         pixels with x or y on the image edge are 0 in every channel (:1164-1176)
+// The edge value is replicated into every channel, alpha included (:1311-1313).
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace gip {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+constexpr int kStripPixels = 120;       // 30 producing lanes x 4 pixels
+
+struct SobelTiling {
+    int strips, bands, band_rows;
+    long long tiles;
+};
+
+struct GrayRow {          // gray of this lane's pixels (0,2), (1,3) and the shifted pairs (-1,1), (2,4)
+    uint64_t A, B, PL, PR;
+};
+
+template <int C>
+struct RowWords { uint32_t w[C]; };
+
+template <int C, bool kVec16>
+__device__ __forceinline__ RowWords<C> load_words(const uint8_t* row, int64_t byte_off, int64_t pitch) {
+    RowWords<C> r;
+    if (C == 4 && kVec16) {
+        if (byte_off >= 0 && byte_off + 16 <= pitch) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + byte_off));
+            r.w[0] = v.x; r.w[1 % C] = v.y; r.w[2 % C] = v.z; r.w[3 % C] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; k++) r.w[k] = 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int64_t o = byte_off + 4 * k;
+            r.w[k] = (o >= 0 && o + 4 <= pitch) ? __ldg(reinterpret_cast<const uint32_t*>(row + o)) : 0u;
+        }
+    }
+    return r;
+}
+
+// byte `idx` (0..4C-1) of the lane's words as the float bit pattern 2^23 + byte
+template <int C>
+__device__ __forceinline__ uint32_t biased_byte(const RowWords<C>& r, int idx) {
+    return __byte_perm(r.w[idx >> 2], 0x4B000000u, 0x7540 | (idx & 3));
+}
+
+template <int C, bool kU8>
+__device__ __forceinline__ GrayRow make_gray(const RowWords<C>& r, int lane) {
+    const uint64_t kNeg23 = splat_f2(-8388608.0f);
+    uint64_t A, B;
+    if (C == 1) {
+        A = add_rn_x2(pack_f2(biased_byte<C>(r, 0), biased_byte<C>(r, 2)), kNeg23);
+        B = add_rn_x2(pack_f2(biased_byte<C>(r, 1), biased_byte<C>(r, 3)), kNeg23);
+    } else {
+        // pixel j: R = byte C*j, G = C*j+1, B = C*j+2
+        const uint64_t RA = add_rn_x2(pack_f2(biased_byte<C>(r, 0), biased_byte<C>(r, 2 * C)), kNeg23);
+        const uint64_t GA = add_rn_x2(pack_f2(biased_byte<C>(r, 1), biased_byte<C>(r, 2 * C + 1)), kNeg23);
+        const uint64_t BA = add_rn_x2(pack_f2(biased_byte<C>(r, 2), biased_byte<C>(r, 2 * C + 2)), kNeg23);
+        const uint64_t RB = add_rn_x2(pack_f2(biased_byte<C>(r, C), biased_byte<C>(r, 3 * C)), kNeg23);
+        const uint64_t GB = add_rn_x2(pack_f2(biased_byte<C>(r, C + 1), biased_byte<C>(r, 3 * C + 1)), kNeg23);
+        const uint64_t BB = add_rn_x2(pack_f2(biased_byte<C>(r, C + 2), biased_byte<C>(r, 3 * C + 2)), kNeg23);
+        const uint64_t kR = splat_f2(0.299f), kG = splat_f2(0.587f), kB = splat_f2(0.114f);
+        A = fma_rn_x2(BA, kB, fma_rn_x2(RA, kR, mul_rn_x2(GA, kG)));
+        B = fma_rn_x2(BB, kB, fma_rn_x2(RB, kR, mul_rn_x2(GB, kG)));
+        if (kU8) {           // (float)(uchar)(gray + 0.5f): add, truncate on the 2^23 grid, remove the bias
+            const uint64_t kHalf = splat_f2(0.5f), k23 = splat_f2(8388608.0f);
+            A = add_rn_x2(add_rz_x2(add_rn_x2(A, kHalf), k23), kNeg23);
+            B = add_rn_x2(add_rz_x2(add_rn_x2(B, kHalf), k23), kNeg23);
+        }
+    }
+    GrayRow g;
+    g.A = A; g.B = B;
+    const uint32_t left = __shfl_up_sync(0xffffffffu, hi_f2(B), 1);     // pixel 3 of lane-1 == pixel -1
+    const uint32_t right = __shfl_down_sync(0xffffffffu, lo_f2(A), 1);  // pixel 0 of lane+1 == pixel 4
+    g.PL = pack_f2(left, lo_f2(B));      // pixels (-1, 1)
+    g.PR = pack_f2(hi_f2(A), right);     // pixels ( 2, 4)
+    (void)lane;
+    return g;
+}
+
+// Sobel magnitude of two pixels, as float bit patterns whose low byte is the rounded u8.
+__device__ __forceinline__ uint64_t sobel_pair(uint64_t TL, uint64_t TC, uint64_t TR, uint64_t ML, uint64_t MR,
+                                               uint64_t BL, uint64_t BC, uint64_t BR) {
+    const uint64_t kM2 = splat_f2(-2.0f), kP2 = splat_f2(2.0f), kZero = splat_f2(0.0f);
+    uint64_t gx = sub_rn_x2(kZero, TL);             // -TL
+    uint64_t gy = fma_rn_x2(TC, kM2, gx);           // -TL - 2TC        (one rounding)
+    gx = add_rn_x2(gx, TR);
+    gy = sub_rn_x2(gy, TR);
+    gx = fma_rn_x2(ML, kM2, gx);
+    gx = fma_rn_x2(MR, kP2, gx);
+    gx = sub_rn_x2(gx, BL);
+    gy = add_rn_x2(gy, BL);
+    gy = fma_rn_x2(BC, kP2, gy);
+    gx = add_rn_x2(gx, BR);
+    gy = add_rn_x2(gy, BR);
+    // fma(gx, gx, gy*gy); the 1e-30 only matters when both gradients are zero (keeps rsqrt finite)
+    const uint64_t m2 = fma_rn_x2(gx, gx, fma_rn_x2(gy, gy, splat_f2(1e-30f)));
+    // sqrtf, the reference's inlined sequence
+    const float r0 = rsqrt_approx(__uint_as_float(lo_f2(m2))), r1 = rsqrt_approx(__uint_as_float(hi_f2(m2)));
+    const uint64_t r = pack_f2(__float_as_uint(r0), __float_as_uint(r1));
+    const uint64_t s0 = mul_rn_x2(m2, r);
+    const uint64_t h = mul_rn_x2(r, splat_f2(0.5f));
+    const uint64_t ns0 = mul_rn_x2(s0, splat_f2(-1.0f));
+    const uint64_t d = fma_rn_x2(ns0, s0, m2);
+    const uint64_t s = fma_rn_x2(d, h, s0);
+    const float m_lo = fminf(__uint_as_float(lo_f2(s)), 255.0f), m_hi = fminf(__uint_as_float(hi_f2(s)), 255.0f);
+    const uint64_t t = add_rn_x2(pack_f2(__float_as_uint(m_lo), __float_as_uint(m_hi)), splat_f2(0.5f));
+    return add_rz_x2(t, splat_f2(8388608.0f));
+}
+
+template <int C, bool kU8, bool kVec16>
+__global__ void __launch_bounds__(kThreads, 4)
+gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTiling tl) {
+    const int lane = threadIdx.x & 31;
+    long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (tile >= tl.tiles) return;
+    const int strip = (int)(tile % tl.strips); tile /= tl.strips;
+    const int band = (int)(tile % tl.bands);
+    const int64_t img = tile / tl.bands;
+    const int64_t W = job.width, H = job.height, pitch = job.src.pitch;
+    const int64_t Y0 = job.src.band_y0 + (int64_t)band * tl.band_rows;
+    const int64_t Y1 = (Y0 + tl.band_rows < job.src.band_y1) ? Y0 + tl.band_rows : job.src.band_y1;
+    if (Y0 >= Y1) return;
+
+    const int64_t x0 = (int64_t)strip * kStripPixels - 4 + 4 * lane;    // first pixel of this lane
+    const int64_t boff = x0 * C;
+    const bool stores = lane >= 1 && lane <= 30;
+    // per-word store predicates and border masks (x == 0, x == W-1 and x >= W give 0 / no store)
+    bool wvalid[C];
+    uint32_t wmask[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        const int64_t o = boff + 4 * k;
+        wvalid[k] = stores && o >= 0 && o + 4 <= pitch;
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int64_t px = (o + b) / C;
+            if (px >= 1 && px <= W - 2) m |= 0xFFu << (8 * b);
+        }
+        wmask[k] = m;
+    }
+
+    auto row_ptr = [&](int64_t y) { return job.src.row(clamp64(y, 0, H - 1), img); };
+    uint8_t* out = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + boff;
+
+    auto emit = [&](const GrayRow& T, const GrayRow& M, const GrayRow& Bt, int64_t y) {
+        uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+        if (y >= 1 && y <= H - 2) {
+            const uint64_t zA = sobel_pair(T.PL, T.A, T.B, M.PL, M.B, Bt.PL, Bt.A, Bt.B);    // pixels 0, 2
+            const uint64_t zB = sobel_pair(T.A, T.B, T.PR, M.A, M.PR, Bt.A, Bt.B, Bt.PR);    // pixels 1, 3
+            z0 = lo_f2(zA); z2 = hi_f2(zA); z1 = lo_f2(zB); z3 = hi_f2(zB);
+        }
+        uint32_t w[C];
+        if (C == 1) {
+            w[0] = __byte_perm(__byte_perm(z0, z1, 0x4040), __byte_perm(z2, z3, 0x4040), 0x5410);
+        } else if (C == 3) {
+            w[0] = __byte_perm(z0, z1, 0x4000); w[1 % C] = __byte_perm(z1, z2, 0x4400); w[2 % C] = __byte_perm(z2, z3, 0x4440);
+        } else {
+            w[0] = __byte_perm(z0, z0, 0x0000); w[1 % C] = __byte_perm(z1, z1, 0x0000);
+            w[2 % C] = __byte_perm(z2, z2, 0x0000); w[3 % C] = __byte_perm(z3, z3, 0x0000);
+        }
+        if (y == 0 || y == H - 1) {
+#pragma unroll
+            for (int k = 0; k < C; k++) w[k] = 0;
+        }
+        if (C == 4 && kVec16) {
+            if (wvalid[0]) stg128_stream(out, make_uint4(w[0] & wmask[0], w[1 % C] & wmask[1 % C], w[2 % C] & wmask[2 % C], w[3 % C] & wmask[3 % C]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; k++)
+                if (wvalid[k]) stg32_stream(out + 4 * k, w[k] & wmask[k]);
+        }
+        out += pitch;
+    };
+
+    // rows Y0-1 and Y0 prime the pipeline; the words of the next row are always in flight
+    GrayRow R0 = make_gray<C, kU8>(load_words<C, kVec16>(row_ptr(Y0 - 1), boff, pitch), lane);
+    GrayRow R1 = make_gray<C, kU8>(load_words<C, kVec16>(row_ptr(Y0), boff, pitch), lane);
+    GrayRow R2;
+    RowWords<C> nxt = load_words<C, kVec16>(row_ptr(Y0 + 1), boff, pitch);
+    for (int64_t y = Y0; y < Y1; y += 3) {
+        // output row y needs rows y-1 (R0), y (R1), y+1 (nxt -> R2)
+        R2 = make_gray<C, kU8>(nxt, lane);
+        nxt = load_words<C, kVec16>(row_ptr(y + 2), boff, pitch);
+        emit(R0, R1, R2, y);
+        if (y + 1 >= Y1) break;
+        R0 = make_gray<C, kU8>(nxt, lane);
+        nxt = load_words<C, kVec16>(row_ptr(y + 3), boff, pitch);
+        emit(R1, R2, R0, y + 1);
+        if (y + 2 >= Y1) break;
+        R1 = make_gray<C, kU8>(nxt, lane);
+        nxt = load_words<C, kVec16>(row_ptr(y + 4), boff, pitch);
+        emit(R2, R0, R1, y + 2);
+    }
+}
+
+int g_num_sms = 0;
+
+template <int C, bool kU8, bool kVec16>
+cudaError_t launch(const Job& job, const SobelTiling& tl, cudaStream_t stream) {
+    const long long blocks = (tl.tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    gip_sobel_fused<C, kU8, kVec16><<<(unsigned)blocks, kThreads, 0, stream>>>(job, tl);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int C>
+cudaError_t launch_c(const Job& job, const SobelTiling& tl, bool vec16, cudaStream_t stream) {
+    if (job.sobel_u8_gray && C != 1)
+        return vec16 ? launch<C, true, true>(job, tl, stream) : launch<C, true, false>(job, tl, stream);
+    return vec16 ? launch<C, false, true>(job, tl, stream) : launch<C, false, false>(job, tl, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    const int C = job.channels;
+    const int64_t pitch = job.src.pitch;
+    // 32-bit word loads/stores: every row must start on a 4-byte boundary
+    const bool aligned4 = (pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.src.band % 4 == 0) &&
+                          ((uintptr_t)job.out % 4 == 0) && (!job.src.above || (uintptr_t)job.src.above % 4 == 0) &&
+                          (!job.src.below || (uintptr_t)job.src.below % 4 == 0);
+    if (!aligned4) return cudaSuccess;               // general path
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    SobelTiling tl;
+    tl.strips = (int)((job.width + kStripPixels - 1) / kStripPixels);
+    const int64_t rows = job.src.band_y1 - job.src.band_y0;
+    if (rows > 0x3fffffff) return cudaSuccess;
+    const int64_t per_band = (int64_t)tl.strips * job.batch;
+    const int64_t want_tiles = (int64_t)g_num_sms * 32 * 2;          // two rounds of 32 resident warps per SM
+    int64_t bands = (want_tiles + per_band - 1) / per_band;
+    int64_t max_bands = rows / 24; if (max_bands < 1) max_bands = 1;  // a band re-reads 2 halo rows
+    if (bands > max_bands) bands = max_bands;
+    if (bands < 1) bands = 1;
+    tl.bands = (int)bands;
+    tl.band_rows = (int)((rows + bands - 1) / bands);
+    tl.tiles = per_band * bands;
+    if ((tl.tiles + kWarpsPerBlock - 1) / kWarpsPerBlock > 0x7fffffffLL) return cudaSuccess;
+    const bool vec16 = (C == 4) && (pitch % 16 == 0) && (job.src.image_stride % 16 == 0) &&
+                       ((uintptr_t)job.src.band % 16 == 0) && ((uintptr_t)job.out % 16 == 0) &&
+                       (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
+                       (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
+    cudaError_t err;
+    if (C == 4)      err = launch_c<4>(job, tl, vec16, stream);
+    else if (C == 3) err = launch_c<3>(job, tl, false, stream);
+    else             err = launch_c<1>(job, tl, false, stream);
+    *handled = (err == cudaSuccess);
+    return err;
+}
+
+}  // namespace gip
