@@ -11,6 +11,7 @@ cudaError_t launch_fast(FilterKind kind, const Job& job, cudaStream_t stream, bo
     *handled = false;
     if (kind == kBox) return launch_fast_box(job, stream, handled);
     if (kind == kSobel) return launch_fast_sobel(job, stream, handled);
+    if (kind == kGaussian) return launch_fast_gauss(job, stream, handled);
     return cudaSuccess;
 }
 

@@ -41,23 +41,17 @@ struct GrayRow {          // gray of this lane's pixels (0,2), (1,3) and the shi
 template <int C>
 struct RowWords { uint32_t w[C]; };
 
+// `off[k]` are in-row byte offsets made safe once per lane (words outside the row read offset 0:
+// their pixels only feed border outputs, which are zero).
 template <int C, bool kVec16>
-__device__ __forceinline__ RowWords<C> load_words(const uint8_t* row, int64_t byte_off, int64_t pitch) {
+__device__ __forceinline__ RowWords<C> load_words(const uint8_t* row, const int (&off)[C]) {
     RowWords<C> r;
     if (C == 4 && kVec16) {
-        if (byte_off >= 0 && byte_off + 16 <= pitch) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + byte_off));
-            r.w[0] = v.x; r.w[1 % C] = v.y; r.w[2 % C] = v.z; r.w[3 % C] = v.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; k++) r.w[k] = 0;
-        }
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + off[0]));
+        r.w[0] = v.x; r.w[1 % C] = v.y; r.w[2 % C] = v.z; r.w[3 % C] = v.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < C; k++) {
-            const int64_t o = byte_off + 4 * k;
-            r.w[k] = (o >= 0 && o + 4 <= pitch) ? __ldg(reinterpret_cast<const uint32_t*>(row + o)) : 0u;
-        }
+        for (int k = 0; k < C; k++) r.w[k] = __ldg(reinterpret_cast<const uint32_t*>(row + off[k]));
     }
     return r;
 }
@@ -127,10 +121,10 @@ __device__ __forceinline__ uint64_t sobel_pair(uint64_t TL, uint64_t TC, uint64_
     const uint64_t ns0 = mul_rn_x2(s0, splat_f2(-1.0f));
     const uint64_t d = fma_rn_x2(ns0, s0, m2);
     const uint64_t s = fma_rn_x2(d, h, s0);
-    const float m_lo = fminf(__uint_as_float(lo_f2(s)), 255.0f), m_hi = fminf(__uint_as_float(hi_f2(s)), 255.0f);
-    const uint64_t t = add_rn_x2(pack_f2(__float_as_uint(m_lo), __float_as_uint(m_hi)), splat_f2(0.5f));
-    return add_rz_x2(t, splat_f2(8388608.0f));
+    // (uchar)(fminf(s, 255) + 0.5f) == min(trunc(s + 0.5f), 255): the clamp moves to the integer side (see emit)
+    return add_rz_x2(add_rn_x2(s, splat_f2(0.5f)), splat_f2(8388608.0f));
 }
+__device__ __forceinline__ uint32_t clamp255(uint32_t z) { return min(z, 0x4B0000FFu); }
 
 template <int C, bool kU8, bool kVec16>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -149,13 +143,16 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     const int64_t x0 = (int64_t)strip * kStripPixels - 4 + 4 * lane;    // first pixel of this lane
     const int64_t boff = x0 * C;
     const bool stores = lane >= 1 && lane <= 30;
-    // per-word store predicates and border masks (x == 0, x == W-1 and x >= W give 0 / no store)
+    // per-word load offsets, store predicates and border masks (x == 0, x == W-1 and x >= W give 0 / no store)
+    int off[C];
     bool wvalid[C];
     uint32_t wmask[C];
 #pragma unroll
     for (int k = 0; k < C; k++) {
         const int64_t o = boff + 4 * k;
-        wvalid[k] = stores && o >= 0 && o + 4 <= pitch;
+        const bool inside = o >= 0 && o + 4 <= pitch;
+        off[k] = inside ? (int)o : 0;
+        wvalid[k] = stores && inside;
         uint32_t m = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -164,57 +161,74 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
         }
         wmask[k] = m;
     }
+    if (C == 4 && kVec16 && !(boff >= 0 && boff + 16 <= pitch)) off[0] = 0;
 
-    auto row_ptr = [&](int64_t y) { return job.src.row(clamp64(y, 0, H - 1), img); };
+    // Row pointers advance by `pitch` inside the band's own rows and are recomputed at the seams
+    // (image top / bottom clamp, rows owned by the neighbours above / below).
+    const int nrows = (int)(Y1 - Y0);
+    const int64_t src_lo = job.src.band_y0, src_hi = job.src.band_y1;
+    const uint8_t* rp;                       // pointer of the row most recently loaded
+    int64_t rp_y;
+    auto next_row = [&](int64_t y) {         // rows are requested in increasing order
+        if (y > src_lo && y < src_hi && y < H && rp_y == y - 1) rp += pitch;
+        else rp = job.src.row(clamp64(y, 0, H - 1), img);
+        rp_y = y;
+        return rp;
+    };
     uint8_t* out = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + boff;
+    const int y_first = (int)Y0;             // image rows fit 31 bits here (checked on the host)
+    const int y_last_interior = (int)(H - 2);
 
-    auto emit = [&](const GrayRow& T, const GrayRow& M, const GrayRow& Bt, int64_t y) {
-        uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0;
-        if (y >= 1 && y <= H - 2) {
+    auto emit = [&](const GrayRow& T, const GrayRow& M, const GrayRow& Bt, int y) {
+        uint32_t w[C];
+        if (y >= 1 && y <= y_last_interior) {
             const uint64_t zA = sobel_pair(T.PL, T.A, T.B, M.PL, M.B, Bt.PL, Bt.A, Bt.B);    // pixels 0, 2
             const uint64_t zB = sobel_pair(T.A, T.B, T.PR, M.A, M.PR, Bt.A, Bt.B, Bt.PR);    // pixels 1, 3
-            z0 = lo_f2(zA); z2 = hi_f2(zA); z1 = lo_f2(zB); z3 = hi_f2(zB);
-        }
-        uint32_t w[C];
-        if (C == 1) {
-            w[0] = __byte_perm(__byte_perm(z0, z1, 0x4040), __byte_perm(z2, z3, 0x4040), 0x5410);
-        } else if (C == 3) {
-            w[0] = __byte_perm(z0, z1, 0x4000); w[1 % C] = __byte_perm(z1, z2, 0x4400); w[2 % C] = __byte_perm(z2, z3, 0x4440);
+            const uint32_t z0 = clamp255(lo_f2(zA)), z2 = clamp255(hi_f2(zA));
+            const uint32_t z1 = clamp255(lo_f2(zB)), z3 = clamp255(hi_f2(zB));
+            if (C == 1) {
+                w[0] = __byte_perm(__byte_perm(z0, z1, 0x4040), __byte_perm(z2, z3, 0x4040), 0x5410);
+            } else if (C == 3) {
+                w[0] = __byte_perm(z0, z1, 0x4000); w[1 % C] = __byte_perm(z1, z2, 0x4400); w[2 % C] = __byte_perm(z2, z3, 0x4440);
+            } else {
+                w[0] = __byte_perm(z0, z0, 0x0000); w[1 % C] = __byte_perm(z1, z1, 0x0000);
+                w[2 % C] = __byte_perm(z2, z2, 0x0000); w[3 % C] = __byte_perm(z3, z3, 0x0000);
+            }
+#pragma unroll
+            for (int k = 0; k < C; k++) w[k] &= wmask[k];
         } else {
-            w[0] = __byte_perm(z0, z0, 0x0000); w[1 % C] = __byte_perm(z1, z1, 0x0000);
-            w[2 % C] = __byte_perm(z2, z2, 0x0000); w[3 % C] = __byte_perm(z3, z3, 0x0000);
-        }
-        if (y == 0 || y == H - 1) {
 #pragma unroll
             for (int k = 0; k < C; k++) w[k] = 0;
         }
         if (C == 4 && kVec16) {
-            if (wvalid[0]) stg128_stream(out, make_uint4(w[0] & wmask[0], w[1 % C] & wmask[1 % C], w[2 % C] & wmask[2 % C], w[3 % C] & wmask[3 % C]));
+            if (wvalid[0]) stg128_stream(out, make_uint4(w[0], w[1 % C], w[2 % C], w[3 % C]));
         } else {
 #pragma unroll
             for (int k = 0; k < C; k++)
-                if (wvalid[k]) stg32_stream(out + 4 * k, w[k] & wmask[k]);
+                if (wvalid[k]) stg32_stream(out + 4 * k, w[k]);
         }
         out += pitch;
     };
 
     // rows Y0-1 and Y0 prime the pipeline; the words of the next row are always in flight
-    GrayRow R0 = make_gray<C, kU8>(load_words<C, kVec16>(row_ptr(Y0 - 1), boff, pitch), lane);
-    GrayRow R1 = make_gray<C, kU8>(load_words<C, kVec16>(row_ptr(Y0), boff, pitch), lane);
+    rp_y = Y0 - 3;
+    GrayRow R0 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0 - 1), off), lane);
+    GrayRow R1 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0), off), lane);
     GrayRow R2;
-    RowWords<C> nxt = load_words<C, kVec16>(row_ptr(Y0 + 1), boff, pitch);
-    for (int64_t y = Y0; y < Y1; y += 3) {
+    RowWords<C> nxt = load_words<C, kVec16>(next_row(Y0 + 1), off);
+    for (int i = 0; i < nrows; i += 3) {
+        const int y = y_first + i;
         // output row y needs rows y-1 (R0), y (R1), y+1 (nxt -> R2)
         R2 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(row_ptr(y + 2), boff, pitch);
+        nxt = load_words<C, kVec16>(next_row((int64_t)y + 2), off);
         emit(R0, R1, R2, y);
-        if (y + 1 >= Y1) break;
+        if (i + 1 >= nrows) break;
         R0 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(row_ptr(y + 3), boff, pitch);
+        nxt = load_words<C, kVec16>(next_row((int64_t)y + 3), off);
         emit(R1, R2, R0, y + 1);
-        if (y + 2 >= Y1) break;
+        if (i + 2 >= nrows) break;
         R1 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(row_ptr(y + 4), boff, pitch);
+        nxt = load_words<C, kVec16>(next_row((int64_t)y + 4), off);
         emit(R2, R0, R1, y + 2);
     }
 }
@@ -257,7 +271,7 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
     SobelTiling tl;
     tl.strips = (int)((job.width + kStripPixels - 1) / kStripPixels);
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
-    if (rows > 0x3fffffff) return cudaSuccess;
+    if (rows > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
     const int64_t per_band = (int64_t)tl.strips * job.batch;
     const int64_t want_tiles = (int64_t)g_num_sms * 32 * 2;          // two rounds of 32 resident warps per SM
     int64_t bands = (want_tiles + per_band - 1) / per_band;
