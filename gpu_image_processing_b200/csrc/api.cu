@@ -18,6 +18,18 @@ static std::atomic<int64_t> g_launches{0};
 static std::atomic<int> g_path{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    int n = cache[dev].load();
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cache[dev].store(n);
+    }
+    return n;
+}
+
 static bool verbose() {
     static const bool v = [] { const char* e = getenv("GIP_VERBOSE"); return e && e[0] == '1'; }();
     return v;
@@ -46,6 +58,22 @@ struct BandArgs {
     int64_t y0 = 0, rows = -1, rows_above = 0, rows_below = 0;
 };
 
+// Stream-ordered scratch (cudaMallocAsync) must not go back to the OS at every synchronisation:
+// keep the default pool's memory cached (set once per device).
+static void keep_pool_cached() {
+    static std::atomic<unsigned long long> done_mask{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (done_mask.load() & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_mask.fetch_or(bit);
+}
+
 // Validate and enqueue one filter.  All entry points funnel through here.
 static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out, int64_t width,
                            int64_t height, int channels, int64_t batch, float sigma, int radius,
@@ -59,6 +87,7 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
     if (kind != kSobel && radius < 0) return cudaErrorInvalidValue;
     if (kind == kGaussian && !(sigma > 0.0f)) return cudaErrorInvalidValue;
     if (kind == kSobel) radius = 1;
+    keep_pool_cached();
 
     Job job;
     memset(&job, 0, sizeof(job));
@@ -313,6 +342,11 @@ int gip_sobel_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int
     return (int)run_host(kSobel, h_input, h_output, width, height, channels, batch, 0.0f, 1, level, metrics);
 }
 
+int gip_device_alloc(int64_t bytes, void** d_ptr_out) {
+    if (bytes <= 0 || !d_ptr_out) return (int)cudaErrorInvalidValue;
+    return (int)cudaMalloc(d_ptr_out, (size_t)bytes);
+}
+int gip_device_free(void* d_ptr) { return (int)cudaFree(d_ptr); }
 int gip_ipc_export(const void* d_ptr, uint8_t handle_out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!d_ptr || !handle_out) return (int)cudaErrorInvalidValue;

@@ -49,6 +49,7 @@ cudaError_t launch_general(FilterKind kind, const Job& job, const float* d_wide_
 cudaError_t launch_fast(FilterKind kind, const Job& job, cudaStream_t stream, bool* handled);
 
 void count_launch(int n = 1);
+int num_sms();   // SM count of the current device (cached per device)
 
 __host__ __device__ __forceinline__ int64_t clamp64(int64_t v, int64_t lo, int64_t hi) {
     return v < lo ? lo : (v > hi ? hi : v);

@@ -1,324 +1,48 @@
-// fast_gauss.cu -- separable Gaussian blur for sm_100a, radius 1..15, weights as kernel parameters.
-//
-// Replaces gaussianBlur{Horizontal,Vertical}{Naive,Level2}
-// (/root/reference/cuda_lib/src/image_filters.cu:64-144, :159-347).  Two kernels, like the reference's
-// two passes, with the reference's u8-rounded intermediate image (:102) between them; the work inside a
-// pass is what changes.  The reference converts and multiplies every neighbour again for every output
-// (2r+1 byte loads + I2F + FFMA per output byte).  Here every input byte is loaded and converted ONCE
-// and scattered into the 2r+1 outputs it belongs to, which live in a rotating set of register
-// accumulators (static register indices by unrolling 2r+1 steps; R = radius is a template parameter):
-//   out[o] accumulates  fma(in[o-r], w[0], 0), fma(in[o-r+1], w[1], .), ... fma(in[o+r], w[2r], .)
-// in exactly the reference's tap order (:86-99), so the float32 sums are bit-identical.
-//   H pass  (gip_gauss_h)  a CTA stages a 64-row x 256-pixel tile (+ r pixels of halo, clamp-to-edge)
-//           in shared memory with cp.async.  A thread owns one channel of a row PAIR and marches
-//           along x: the two rows are the two lanes of FFMA2, so one issue slot does two taps.  Lanes of
-//           a warp are 32 different row pairs (odd shared-memory pitch: conflict-free byte loads).
-//           Rounded bytes go to an output tile in shared memory and leave with coalesced 32-bit stores.
-//   V pass  (gip_gauss_v)  a thread owns a 4-byte column group and marches down a band of rows straight
-//           from global memory (coalesced 32-bit loads); adjacent bytes are the FFMA2 lanes.
-// Rounding: (uchar)(sum + 0.5f) (:102, :142) == low mantissa byte of RZ((sum + 0.5f) + 2^23).
-// u8 -> float: PRMT into the mantissa of 2^23, minus 2^23 (exact), two values per FADD2.
-// The algorithm is FP32-issue bound, not HBM bound, from radius 3 up (4r+2 FMAs per byte); DESIGN.md
-// carries the instruction roofline next to the HBM one.
+// fast_gauss.cu -- dispatch of the fused Gaussian path by radius (kernels: fast_gauss_impl.cuh).
 #include "common.cuh"
-#include "device_utils.cuh"
 
 namespace gip {
-namespace {
 
-constexpr int kMaxFastRadius = 15;
-constexpr int kTileRows = 64;           // H pass: 32 row pairs (rows l and l+32 are one lane's pair)
-constexpr int kSegPixels = 128;         // H pass: pixels per thread segment
-
-template <int C> struct HCfg {
-    static constexpr int kSegs = (C == 1) ? 8 : 2;
-    static constexpr int kTilePixels = kSegs * kSegPixels;
-    static constexpr int kThreads = 32 * C * kSegs;
-};
-
-__device__ __forceinline__ uint64_t to_float_pair(uint32_t lo_byte, uint32_t hi_byte) {
-    // bytes (already zero-extended) -> floats: OR into the mantissa of 2^23, subtract 2^23
-    return add_rn_x2(pack_f2(lo_byte | 0x4B000000u, hi_byte | 0x4B000000u), splat_f2(-8388608.0f));
-}
-__device__ __forceinline__ uint64_t round_pair(uint64_t acc) {
-    return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
-}
-
-// ------------------------------------------------------------------------------------------------
-// H pass.  Image rows [ty0, ty1) of every image of the chunk -> scratch image `tmp` (same pitch).
-// ------------------------------------------------------------------------------------------------
-template <int R, int C, bool kVec>
-__global__ void __launch_bounds__(HCfg<C>::kThreads, 1)
-gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
-            int64_t img0, int tiles_x, int tiles_y, int in_pitch, int out_pitch) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int R2 = 2 * R + 1;
-    constexpr int TW = HCfg<C>::kTilePixels;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t W = job.width, pitch = job.src.pitch;
-    unsigned t = blockIdx.x;
-    const int tx = (int)(t % (unsigned)tiles_x); t /= (unsigned)tiles_x;
-    const int ty = (int)(t % (unsigned)tiles_y);
-    const int64_t img = img0 + t / (unsigned)tiles_y;
-    const int64_t row0 = ty0 + (int64_t)ty * kTileRows;
-    const int nrows = (int)((ty1 - row0) < kTileRows ? (ty1 - row0) : kTileRows);
-    const int64_t gx0 = (int64_t)tx * TW;                       // first output pixel of the tile
-    const int64_t b0 = (gx0 - R) * C;                           // image-row byte position of tile byte 0
-    const int tile_bytes = (TW + 2 * R) * C;
-    const int skew = kVec ? (int)(((b0 % 4) + 4) % 4) : 0;      // keeps 4-byte chunks aligned on both sides
-    uint8_t* in_tile = smem;
-    uint8_t* out_tile = smem + (size_t)kTileRows * in_pitch;
-
-    // ---- stage: bytes [lo, hi) of each row are real image bytes, the rest is clamp-to-edge replication
-    const int64_t lo = b0 < 0 ? 0 : b0;
-    int64_t hi = b0 + tile_bytes; if (hi > pitch) hi = pitch;
-    if (kVec) {
-        // 4-byte cp.async: the odd-word row pitch that makes the byte loads conflict-free rules out 16-byte chunks
-        const int64_t cs = lo & ~int64_t(3);
-        int64_t ce = (hi + 3) & ~int64_t(3); if (ce > pitch) ce = pitch;
-        const int nchunk = ce > cs ? (int)((ce - cs) >> 2) : 0;
-        const uint32_t in_s = smem_addr(in_tile);
-        for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
-            const uint8_t* src = job.src.row(row0 + rr, img) + cs;
-            const uint32_t dst = in_s + (uint32_t)(rr * in_pitch + skew + (int)(cs - b0));
-            for (int ci = lane; ci < nchunk; ci += 32) cp_async4(dst + 4 * ci, src + 4 * ci);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-    } else {
-        const int n = hi > lo ? (int)(hi - lo) : 0;
-        for (int idx = tid; idx < n * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / n, i = idx - rr * n;
-            in_tile[rr * in_pitch + (int)(lo - b0) + i] = job.src.row(row0 + rr, img)[lo + i];
-        }
-    }
-    __syncthreads();
-    {   // replicate the edge pixel into the halo outside the image (left of pixel 0, right of pixel W-1)
-        const int nl = b0 < 0 ? (int)(-b0) : 0;
-        const int nr = (b0 + tile_bytes > pitch) ? (int)(b0 + tile_bytes - pitch) : 0;
-        const int first_r = tile_bytes - nr;
-        for (int idx = tid; idx < (nl + nr) * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / (nl + nr), i = idx - rr * (nl + nr);
-            uint8_t* rowp = in_tile + rr * in_pitch + skew;
-            if (i < nl) rowp[i] = rowp[nl + (i % C)];                                   // b0 is a multiple of C
-            else { const int k = i - nl; rowp[first_r + k] = rowp[first_r - C + (k % C)]; }
-        }
-    }
-    __syncthreads();
-
-    // ---- march: this thread = (row pair, channel, segment)
-    {
-        const int ch = warp % C, seg = warp / C;
-        const int ra = lane, rb = lane + 32;
-        const bool has_a = ra < nrows, has_b = rb < nrows;
-        const uint8_t* pa = in_tile + (has_a ? ra : 0) * in_pitch + skew + seg * kSegPixels * C + ch;
-        const uint8_t* pb = in_tile + (has_b ? rb : 0) * in_pitch + skew + seg * kSegPixels * C + ch;
-        uint8_t* qa = out_tile + ra * out_pitch + seg * kSegPixels * C + ch;
-        uint8_t* qb = out_tile + rb * out_pitch + seg * kSegPixels * C + ch;
-        uint64_t acc[R2];
-#pragma unroll
-        for (int i = 0; i < R2; i++) acc[i] = 0;
-        constexpr int kSteps = kSegPixels + 2 * R;       // input pixels seg*128 - R ... seg*128 + 127 + R (tile-relative +R)
-        for (int s0 = 0; s0 < kSteps; s0 += R2) {
-#pragma unroll
-            for (int u = 0; u < R2; u++) {
-                const int s = s0 + u;
-                if (s < kSteps) {
-                    const uint64_t v = to_float_pair(pa[s * C], pb[s * C]);
-                    acc[u] = mul_rn_x2(v, splat_f2(job.weights[0]));                       // tap 0: fma(v, w0, 0)
-#pragma unroll
-                    for (int k = 1; k < R2; k++)
-                        acc[(u - k + R2) % R2] = fma_rn_x2(v, splat_f2(job.weights[k]), acc[(u - k + R2) % R2]);
-                    if (s >= 2 * R) {                                                       // output pixel s - 2R is complete
-                        const uint64_t z = round_pair(acc[(u + 1) % R2]);
-                        const int o = (s - 2 * R) * C;
-                        qa[o] = (uint8_t)lo_f2(z);
-                        qb[o] = (uint8_t)hi_f2(z);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- copy the output tile to the scratch image
-    const int64_t ob0 = gx0 * C;
-    int64_t out_bytes = (int64_t)TW * C; if (ob0 + out_bytes > pitch) out_bytes = pitch - ob0;
-    uint8_t* tbase = tmp + ((img - img0) * (ty1 - ty0) + (row0 - ty0)) * pitch + ob0;
-    if (kVec) {            // the odd shared-memory pitch keeps rows word-aligned only: 32-bit copies
-        const int nv = (int)(out_bytes >> 2);
-        for (int idx = tid; idx < nv * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / nv, ci = idx - rr * nv;
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(out_tile + rr * out_pitch + 4 * ci);
-            *reinterpret_cast<uint32_t*>(tbase + (int64_t)rr * pitch + 4 * ci) = v;
-        }
-    } else {
-        const int n = (int)out_bytes;
-        for (int idx = tid; idx < n * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / n, i = idx - rr * n;
-            tbase[(int64_t)rr * pitch + i] = out_tile[rr * out_pitch + i];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// V pass.  Scratch rows -> output rows [band_y0, band_y1).  One thread per 4-byte column group.
-// ------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(128)
-gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
-            int64_t img0, int nbands, int band_rows, int words) {
-    constexpr int R2 = 2 * R + 1;
-    const int64_t pitch = job.src.pitch;
-    const int wi = blockIdx.x * 128 + threadIdx.x;
-    if (wi >= words) return;
-    const int band = blockIdx.y % nbands;
-    const int64_t li = blockIdx.y / nbands;                       // image index inside the chunk
-    const int64_t Y0 = job.src.band_y0 + (int64_t)band * band_rows;
-    const int64_t Y1 = (Y0 + band_rows < job.src.band_y1) ? Y0 + band_rows : job.src.band_y1;
-    if (Y0 >= Y1) return;
-    const uint8_t* timg = tmp + li * (ty1 - ty0) * pitch + 4 * (int64_t)wi;
-    uint8_t* optr = job.out + (img0 + li) * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + 4 * (int64_t)wi;
-    const int64_t H = job.height;
-
-    uint64_t acc0[R2], acc1[R2];
-#pragma unroll
-    for (int i = 0; i < R2; i++) { acc0[i] = 0; acc1[i] = 0; }
-    const int nsteps = (int)(Y1 - Y0) + 2 * R;                    // input rows Y0-R .. Y1-1+R (clamped to the image)
-    auto load = [&](int s) {
-        const int64_t y = clamp64(Y0 - R + s, 0, H - 1);
-        return __ldg(reinterpret_cast<const uint32_t*>(timg + (y - ty0) * pitch));
-    };
-    uint32_t nxt = load(0);
-    for (int s0 = 0; s0 < nsteps; s0 += R2) {
-#pragma unroll
-        for (int u = 0; u < R2; u++) {
-            const int s = s0 + u;
-            if (s < nsteps) {
-                const uint32_t w = nxt;
-                if (s + 1 < nsteps) nxt = load(s + 1);
-                const uint64_t v0 = to_float_pair(w & 0xFFu, (w >> 8) & 0xFFu);
-                const uint64_t v1 = to_float_pair((w >> 16) & 0xFFu, w >> 24);
-                acc0[u] = mul_rn_x2(v0, splat_f2(job.weights[0]));
-                acc1[u] = mul_rn_x2(v1, splat_f2(job.weights[0]));
-#pragma unroll
-                for (int k = 1; k < R2; k++) {
-                    const uint64_t wk = splat_f2(job.weights[k]);
-                    acc0[(u - k + R2) % R2] = fma_rn_x2(v0, wk, acc0[(u - k + R2) % R2]);
-                    acc1[(u - k + R2) % R2] = fma_rn_x2(v1, wk, acc1[(u - k + R2) % R2]);
-                }
-                if (s >= 2 * R) {
-                    const uint64_t z0 = round_pair(acc0[(u + 1) % R2]), z1 = round_pair(acc1[(u + 1) % R2]);
-                    const uint32_t t0 = __byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), t1 = __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040);
-                    stg32_stream(optr, __byte_perm(t0, t1, 0x5410));
-                    optr += pitch;
-                }
-            }
-        }
-    }
-}
-
-int g_num_sms = 0;
-
-template <int R, int C>
-cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t ty0, int64_t ty1, int64_t img0, int64_t nimg, bool vec,
-                     cudaStream_t stream) {
-    constexpr int TW = HCfg<C>::kTilePixels;
-    const int tiles_x = (int)((job.width + TW - 1) / TW);
-    const int tiles_y = (int)((ty1 - ty0 + kTileRows - 1) / kTileRows);
-    int in_pitch = ((TW + 2 * R) * C + 32 + 3) & ~3;            // + skew and chunk-rounding room, whole words
-    if (((in_pitch >> 2) & 1) == 0) in_pitch += 4;                // odd number of words: conflict-free across rows
-    int out_pitch = (TW * C + 15) & ~15;
-    out_pitch += 4;                                               // TW*C/4 is even: +1 word makes the pitch odd
-    const size_t smem = (size_t)kTileRows * (in_pitch + out_pitch);
-    const int64_t blocks = (int64_t)tiles_x * tiles_y * nimg;
-    if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (vec) {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, true><<<(unsigned)blocks, HCfg<C>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch);
-    } else {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, false><<<(unsigned)blocks, HCfg<C>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch);
-    }
-    count_launch();
-    return cudaGetLastError();
-}
-
-template <int R>
-cudaError_t launch_v(const Job& job, const uint8_t* tmp, int64_t ty0, int64_t ty1, int64_t img0, int64_t nimg,
-                     cudaStream_t stream) {
-    const int words = (int)(job.src.pitch / 4);
-    const int64_t rows = job.src.band_y1 - job.src.band_y0;
-    const int64_t col_blocks = (words + 127) / 128;
-    // enough bands to fill the machine (each band re-reads 2R scratch rows)
-    int64_t want = ((int64_t)g_num_sms * 16 + col_blocks * nimg - 1) / (col_blocks * nimg);
-    int64_t max_bands = rows / (4 * (2 * R + 1)); if (max_bands < 1) max_bands = 1;
-    if (want > max_bands) want = max_bands;
-    if (want < 1) want = 1;
-    const int nbands = (int)want;
-    const int band_rows = (int)((rows + nbands - 1) / nbands);
-    if (nbands * nimg > 65535) return cudaErrorInvalidValue;
-    dim3 grid((unsigned)col_blocks, (unsigned)(nbands * nimg));
-    gip_gauss_v<R><<<grid, 128, 0, stream>>>(job, tmp, ty0, ty1, img0, nbands, band_rows, words);
-    count_launch();
-    return cudaGetLastError();
-}
-
-template <int R>
-cudaError_t run_radius(const Job& job, cudaStream_t stream) {
-    const int C = job.channels;
-    const int64_t pitch = job.src.pitch;
-    const int64_t ty0 = clamp64(job.src.band_y0 - R, 0, job.height);
-    const int64_t ty1 = clamp64(job.src.band_y1 + R, 0, job.height);
-    const int64_t trows = ty1 - ty0;
-    const bool vec = (pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.src.band % 4 == 0) &&
-                     (!job.src.above || (uintptr_t)job.src.above % 4 == 0) &&
-                     (!job.src.below || (uintptr_t)job.src.below % 4 == 0);
-    // scratch: whole images of the batch, at most ~1 GiB at a time (and at most 8192 images: grid.y)
-    int64_t chunk = (int64_t(1) << 30) / (trows * pitch);
-    if (chunk < 1) chunk = 1;
-    if (chunk > job.batch) chunk = job.batch;
-    if (chunk > 2048) chunk = 2048;
-    uint8_t* tmp = nullptr;
-    cudaError_t err = cudaMallocAsync((void**)&tmp, (size_t)(chunk * trows * pitch), stream);
-    if (err != cudaSuccess) return err;
-    for (int64_t img0 = 0; img0 < job.batch && err == cudaSuccess; img0 += chunk) {
-        const int64_t n = (job.batch - img0 < chunk) ? job.batch - img0 : chunk;
-        if (C == 4)      err = launch_h<R, 4>(job, tmp, ty0, ty1, img0, n, vec, stream);
-        else if (C == 3) err = launch_h<R, 3>(job, tmp, ty0, ty1, img0, n, vec, stream);
-        else             err = launch_h<R, 1>(job, tmp, ty0, ty1, img0, n, vec, stream);
-        if (err == cudaSuccess) err = launch_v<R>(job, tmp, ty0, ty1, img0, n, stream);
-    }
-    cudaError_t ferr = cudaFreeAsync(tmp, stream);
-    return err != cudaSuccess ? err : ferr;
-}
-
-}  // namespace
+cudaError_t gauss_run_r01(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r02(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r03(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r04(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r05(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r06(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r07(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r08(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r09(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r10(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r11(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r12(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r13(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r14(const Job& job, cudaStream_t stream);
+cudaError_t gauss_run_r15(const Job& job, cudaStream_t stream);
 
 cudaError_t launch_fast_gauss(const Job& job, cudaStream_t stream, bool* handled) {
     *handled = false;
     const int r = job.radius;
-    if (r < 1 || r > kMaxFastRadius) return cudaSuccess;
+    if (r < 1 || r > 15) return cudaSuccess;
     const int64_t pitch = job.src.pitch;
-    // the V pass loads and stores 32-bit words
-    if (pitch % 4 != 0 || job.src.image_stride % 4 != 0 || (uintptr_t)job.out % 4 != 0) return cudaSuccess;
     if (job.src.band_y1 - job.src.band_y0 > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    if (num_sms() <= 0) return cudaErrorInvalidDevice;
     cudaError_t err;
     switch (r) {
-#define GIP_CASE(N) case N: err = run_radius<N>(job, stream); break;
-        GIP_CASE(1) GIP_CASE(2) GIP_CASE(3) GIP_CASE(4) GIP_CASE(5) GIP_CASE(6) GIP_CASE(7) GIP_CASE(8)
-        GIP_CASE(9) GIP_CASE(10) GIP_CASE(11) GIP_CASE(12) GIP_CASE(13) GIP_CASE(14) GIP_CASE(15)
-#undef GIP_CASE
+        case 1: err = gauss_run_r01(job, stream); break;
+        case 2: err = gauss_run_r02(job, stream); break;
+        case 3: err = gauss_run_r03(job, stream); break;
+        case 4: err = gauss_run_r04(job, stream); break;
+        case 5: err = gauss_run_r05(job, stream); break;
+        case 6: err = gauss_run_r06(job, stream); break;
+        case 7: err = gauss_run_r07(job, stream); break;
+        case 8: err = gauss_run_r08(job, stream); break;
+        case 9: err = gauss_run_r09(job, stream); break;
+        case 10: err = gauss_run_r10(job, stream); break;
+        case 11: err = gauss_run_r11(job, stream); break;
+        case 12: err = gauss_run_r12(job, stream); break;
+        case 13: err = gauss_run_r13(job, stream); break;
+        case 14: err = gauss_run_r14(job, stream); break;
+        case 15: err = gauss_run_r15(job, stream); break;
         default: return cudaSuccess;
     }
     *handled = (err == cudaSuccess);

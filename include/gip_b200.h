@@ -104,9 +104,12 @@ int gip_sobel_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int
                    int channels, int64_t batch, int level, gip_metrics* metrics);
 
 /* ---- peer memory for row bands across processes (CUDA IPC) --------------------------------
- * gip_ipc_export writes a 64-byte handle for a cudaMalloc'ed base pointer; another process on
+ * gip_device_alloc returns plain cudaMalloc memory (framework caching allocators sub-allocate, and CUDA IPC
+ * exports whole allocations).  gip_ipc_export writes a 64-byte handle for such a base pointer; another process on
  * the same node opens it with gip_ipc_open and may pass the mapped pointer as d_above/d_below.
  * gip_enable_peer_access enables P2P from the current device to `peer_device`. */
+int gip_device_alloc(int64_t bytes, void** d_ptr_out);   /* cudaMalloc: a whole allocation, exportable with gip_ipc_export */
+int gip_device_free(void* d_ptr);
 int gip_ipc_export(const void* d_ptr, uint8_t handle_out[64]);
 int gip_ipc_open(const uint8_t handle[64], void** d_ptr_out);
 int gip_ipc_close(void* d_ptr);
