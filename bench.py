@@ -50,6 +50,15 @@ CONFIG = {"workload": "c2: box blur radius sweep r=1..31, 4096x4096 RGBA u8, one
           "sharding": "independent image batches per GPU, no collective"}
 
 
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write of one gip_box_fused launch, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -66,30 +75,45 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi and wait (at most 5 s) for its first sample, so that short timed regions are covered."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t = time.time()
+            while not self.rows and time.time() - t < 5.0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.1)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm),
+                "window": "nvidia-smi every 50 ms over the device-timed region and the end-to-end region"}
 
 
 def cpu_port_run(steps, warmup, rows=1024):
@@ -243,6 +267,7 @@ def main():
     launches0 = L.gip_launch_count()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for k in range(args.steps):
         step(k)
@@ -250,7 +275,6 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = L.gip_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,6 +305,8 @@ def main():
     e2e_s = float(t.item())
     e2e_value = world * H * W * len(RADII) * e2e_steps / e2e_s / 1e6
     img_bytes = H * W * C
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -296,7 +322,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gip_box_fused<4,true>", "peak_source": peak_src,
+                         "traffic": (measured_traffic() or {}).get("bytes_per_launch"), "traffic_source": (measured_traffic() or {}).get("source"),
+                         "kernel": "gip_box_fused<4,true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 2 * img_bytes, "us_per_launch": us_per_launch,
                          "frac_of_8TBs_nominal": achieved / 8000.0},
         }

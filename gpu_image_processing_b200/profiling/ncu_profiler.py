@@ -1,0 +1,189 @@
+"""Nsight Compute side-car: re-runs one filter call under `ncu` in a child process and returns its metrics.
+
+Same three public functions and the same result shape as the reference's backend/profiling/ncu_profiler.py
+(check_ncu_available :25, profile_kernel_with_ncu :39, get_common_ncu_metrics :795): a dict with the
+categories "occupancy", "memory", "warp", "execution", "throughput", "config", "kernel_durations" plus
+"total_kernel_duration_ms", "kernels_profiled", "total_kernels".  `/api/process-all` merges it into the
+response metrics the way app.py:370-430 does.
+
+Differences from the reference: the kernel-name patterns are this library's kernels (the reference matched
+its own names, ncu_profiler.py:72-90); the report is read back as the raw CSV page with exact metric names
+instead of unit heuristics (:499-557); durations come from gpu__time_duration, never from cycles and an
+`nvidia-smi` clock (:598-613); the temporary directory is removed (:320-324 leaks it); achieved DRAM bytes
+and GB/s are added to "memory" because HBM traffic is what these kernels are judged on.
+"""
+from __future__ import annotations
+
+import csv
+import io
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+# filter -> regex over this library's kernel names (fused path and general path)
+KERNEL_PATTERNS = {
+    "gaussian": "regex:gip_(gauss_h|gauss_v|blur_h_general|blur_v_general)",
+    "box": "regex:gip_(box_fused|blur_h_general|blur_v_general)",
+    "sobel": "regex:gip_sobel_(fused|general)",
+}
+
+_CATEGORY_OF = (
+    ("occupancy", ("sm__warps_active", "launch__occupancy", "sm__maximum_warps", "smsp__warps_eligible", "smsp__warps_active")),
+    ("memory", ("dram__", "lts__", "l1tex__", "gpu__dram_throughput", "smsp__inst_executed_op_shared")),
+    ("warp", ("smsp__average_warp", "smsp__warp_issue_stalled", "smsp__thread_inst_executed_per_inst")),
+    ("execution", ("smsp__inst_executed", "smsp__issue_active", "sm__inst_executed", "smsp__cycles_active", "sm__cycles")),
+    ("throughput", ("sm__throughput", "gpu__compute_memory_throughput", "sm__pipe", "sm__inst_executed_pipe")),
+    ("config", ("launch__",)),
+)
+
+
+def check_ncu_available() -> bool:
+    """True when `ncu --version` runs (reference: ncu_profiler.py:25-36)."""
+    try:
+        return subprocess.run(["ncu", "--version"], capture_output=True, text=True, timeout=10).returncode == 0
+    except (FileNotFoundError, subprocess.TimeoutExpired, OSError):
+        return False
+
+
+def _child_script(filter_type: str, level: int, sigma, radius) -> str:
+    call = {"gaussian": f"gpu_filters.gaussian_blur(img, sigma={float(sigma if sigma is not None else 2.0)!r}, radius={int(radius)}, level={int(level)})",
+            "box": f"gpu_filters.box_blur(img, radius={int(radius)}, level={int(level)})",
+            "sobel": f"gpu_filters.sobel_edge_detection(img, level={int(level)})"}[filter_type]
+    return ("import sys\n"
+            f"sys.path.insert(0, {_PKG_ROOT!r})\n"
+            "import numpy as np\n"
+            "from gpu_image_processing_b200 import gpu_filters\n"
+            "img = np.load(sys.argv[1])\n"
+            "for _ in range(3):\n"
+            f"    r = {call}\n"
+            "print('profiled', r['time_ms'])\n")
+
+
+def parse_ncu_raw_csv(text: str) -> Dict[str, Any]:
+    """`ncu --page raw --csv` -> the reference's categorised dict.  One CSV row per kernel launch."""
+    metrics: Dict[str, Any] = {"occupancy": {}, "memory": {}, "warp": {}, "execution": {}, "throughput": {},
+                               "config": {}, "kernel_durations": {}}
+    rows = list(csv.reader(io.StringIO(text[text.find('"ID"'):] if '"ID"' in text else text)))
+    if len(rows) < 3:
+        return metrics
+    header, units, launches = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(header)}
+    per_kernel: Dict[str, list] = {}
+    for row in launches:
+        if len(row) != len(header):
+            continue
+        name = row[col["Kernel Name"]].split("(")[0].strip() if "Kernel Name" in col else "kernel"
+        dur_i = col.get("gpu__time_duration.sum")
+        if dur_i is not None:
+            try:
+                v = float(row[dur_i].replace(",", ""))
+                unit = units[dur_i]
+                ms = v / 1e6 if unit in ("nsecond", "ns") else v / 1e3 if unit in ("usecond", "us") else v if unit in ("msecond", "ms") else v * 1e3
+                per_kernel.setdefault(name, []).append(ms)
+            except ValueError:
+                pass
+    last = launches[-1]
+    for h, i in col.items():
+        if i >= len(last):
+            continue
+        try:
+            val: Any = float(last[i].replace(",", ""))
+        except ValueError:
+            continue
+        for cat, prefixes in _CATEGORY_OF:
+            if h.startswith(prefixes):
+                metrics[cat][f"{h} [{units[i]}]" if units[i] else h] = val
+                break
+    if "launch__block_size" in col:
+        metrics["config"]["block_size"] = last[col["launch__block_size"]]
+    if "launch__grid_size" in col:
+        metrics["config"]["grid_size"] = last[col["launch__grid_size"]]
+    # one filter call = one launch of every kernel in `per_kernel`: average the launches of each kernel
+    metrics["kernel_durations"] = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+    metrics["total_kernel_duration_ms"] = sum(metrics["kernel_durations"].values())
+    metrics["kernels_profiled"] = list(metrics["kernel_durations"].keys())
+    metrics["total_kernels"] = len(metrics["kernel_durations"])
+    rd, wr = col.get("dram__bytes_read.sum"), col.get("dram__bytes_write.sum")
+    if rd is not None and wr is not None and metrics["total_kernel_duration_ms"] > 0:
+        def to_bytes(i):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+            return sum(float(r[i].replace(",", "")) for r in launches if len(r) == len(header)) * scale / max(1, len(launches))
+        per_launch = to_bytes(rd) + to_bytes(wr)
+        metrics["memory"]["dram_bytes_per_launch"] = per_launch
+    return metrics
+
+
+def profile_kernel_with_ncu(img_array: np.ndarray, filter_type: str, level: int, sigma: Optional[float] = None,
+                            radius: Optional[int] = 3) -> Dict[str, Any]:
+    """Profile one filter call (reference signature: ncu_profiler.py:39-45)."""
+    if filter_type not in KERNEL_PATTERNS:
+        raise ValueError(f"unknown filter {filter_type!r}")
+    if not check_ncu_available():
+        raise RuntimeError("ncu (Nsight Compute) not found in PATH. Please install Nsight Compute.")
+    tmpdir = tempfile.mkdtemp(prefix="ncu_profile_")
+    try:
+        npy = os.path.join(tmpdir, "input.npy")
+        np.save(npy, np.ascontiguousarray(img_array, dtype=np.uint8))
+        script = os.path.join(tmpdir, "profile_kernel.py")
+        with open(script, "w") as f:
+            f.write(_child_script(filter_type, level, sigma, radius if radius is not None else 3))
+        rep = os.path.join(tmpdir, "profile")
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--kernel-name", KERNEL_PATTERNS[filter_type],
+               "--launch-skip", "0", "--launch-count", "10", "--export", rep, "--force-overwrite", sys.executable, script, npy]
+        run = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        if run.returncode != 0 or not os.path.exists(rep + ".ncu-rep"):
+            raise RuntimeError(f"ncu failed (rc={run.returncode}): {(run.stderr or run.stdout)[-400:]}")
+        page = subprocess.run(["ncu", "--import", rep + ".ncu-rep", "--page", "raw", "--csv"], capture_output=True,
+                              text=True, timeout=300)
+        if page.returncode != 0:
+            raise RuntimeError(f"ncu --import failed: {page.stderr[-400:]}")
+        metrics = parse_ncu_raw_csv(page.stdout)
+        metrics["filter"], metrics["level"] = filter_type, int(level)
+        return metrics
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+def get_common_ncu_metrics(metrics: Dict[str, Any], ncu_data: Optional[Dict] = None) -> Dict[str, Any]:
+    """Flat summary for the UI table (reference: ncu_profiler.py:795-934), same keys."""
+    if not metrics or not isinstance(metrics, dict):
+        return {}
+    common: Dict[str, Any] = {}
+
+    def first(cat, needle):
+        for k, v in metrics.get(cat, {}).items():
+            if needle in k and isinstance(v, (int, float)):
+                return float(v)
+        return None
+
+    for key, cat, needle in (
+            ("occupancy_pct", "occupancy", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            ("active_warps_per_scheduler", "occupancy", "smsp__warps_active.avg.per_cycle_active"),
+            ("eligible_warps_per_scheduler", "occupancy", "smsp__warps_eligible.avg.per_cycle_active"),
+            ("dram_throughput_pct", "memory", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("memory_throughput_pct", "memory", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("l2_hit_rate_pct", "memory", "lts__t_sector_hit_rate.pct"),
+            ("dram_bytes_per_launch", "memory", "dram_bytes_per_launch"),
+            ("compute_throughput_pct", "throughput", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("issue_active_pct", "execution", "smsp__issue_active.avg.pct_of_peak_sustained_active")):
+        v = first(cat, needle)
+        if v is not None:
+            common[key] = v
+    src = ncu_data if ncu_data and "total_kernel_duration_ms" in ncu_data else metrics
+    if "total_kernel_duration_ms" in src:
+        common["time_ms"] = src["total_kernel_duration_ms"]
+        common["kernel_duration_ms"] = src["total_kernel_duration_ms"]
+        if "kernels_profiled" in src:
+            common["kernels_profiled"] = src["kernels_profiled"]
+            common["total_kernels"] = len(src["kernels_profiled"])
+        if common.get("dram_bytes_per_launch") and common["time_ms"] > 0:
+            common["achieved_dram_gbps"] = common["dram_bytes_per_launch"] * max(1, common.get("total_kernels", 1)) / (common["time_ms"] / 1e3) / 1e9
+    return common
