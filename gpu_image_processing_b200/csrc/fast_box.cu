@@ -257,24 +257,32 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         __syncthreads();          // matches the consumers' last barrier
     } else {
         // ==================================== consumer warp ====================================
+        // Thread vt owns the 4-byte column groups vt, vt + nvt, vt + 2 nvt of the strip (nvt = useful / 12): every
+        // LDS.32 / STG.32 of a warp then covers 32 consecutive words (full 128-byte lines, no partial sectors).
         const int vt = tid - 32 * kHWarps;
         const int nvt = tl.useful / kGroupBytes;
-        const int64_t col = bxs + (int64_t)kGroupBytes * vt;
-        int vbytes = 0;
-        if (vt < nvt && col < pitch) vbytes = (pitch - col >= kGroupBytes) ? kGroupBytes : (int)(pitch - col);
+        int vbytes[3];
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            const int64_t c = bxs + 4 * (int64_t)(vt + w * nvt);
+            vbytes[w] = (vt < nvt && c < pitch) ? ((pitch - c >= 4) ? 4 : (int)(pitch - c)) : 0;
+            any |= vbytes[w] > 0;
+        }
         uint32_t S[kGroupBytes];
 #pragma unroll
         for (int i = 0; i < kGroupBytes; i++) S[i] = kBias;
-        uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;  // next output row
-        const uint32_t ring_tid = ring_s + (uint32_t)(kGroupBytes * vt);
+        const int wstride = 4 * nvt;                     // bytes between this thread's column groups
+        uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + bxs + 4 * (int64_t)vt;  // next output row
+        const uint32_t ring_tid = ring_s + 4u * (uint32_t)(vt < nvt ? vt : 0);
 
         auto v_row = [&](uint32_t a_in, uint32_t a_out, bool leave, bool store) {
             uint32_t res[3];
 #pragma unroll
             for (int w = 0; w < 3; w++) {
-                const uint32_t iw = lds32(a_in + 4 * w);
+                const uint32_t iw = lds32(a_in + w * wstride);
                 uint32_t ow = 0;
-                if (leave) ow = lds32(a_out + 4 * w);
+                if (leave) ow = lds32(a_out + w * wstride);
                 const uint32_t pa = __byte_perm(iw, ow, 0x5140);
                 const uint32_t pb = __byte_perm(iw, ow, 0x7362);
                 S[4 * w + 0] = (uint32_t)dp4a_us(pa, 0x0000FF01, (int)S[4 * w + 0]);
@@ -284,12 +292,13 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                 if (store) res[w] = round_pack(S[4 * w], S[4 * w + 1], S[4 * w + 2], S[4 * w + 3], mag_a2, mag_c2);
             }
             if (store) {
-                if (kVec) {
-                    stg32_stream(optr, res[0]);
-                    if (vbytes > 4) stg32_stream(optr + 4, res[1]);
-                    if (vbytes > 8) stg32_stream(optr + 8, res[2]);
-                } else {
-                    for (int b = 0; b < vbytes; b++) optr[b] = (uint8_t)(res[b >> 2] >> (8 * (b & 3)));
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    if (kVec) {
+                        if (vbytes[w]) stg32_stream(optr + w * wstride, res[w]);
+                    } else {
+                        for (int b = 0; b < vbytes[w]; b++) optr[w * wstride + b] = (uint8_t)(res[w] >> (8 * b));
+                    }
                 }
                 optr += pitch;
             }
@@ -300,7 +309,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         int slot_out = tl.ring_rows - (2 * r + 1);                  // ring slot of (first row - (2r+1))
         for (int step = 0; step < nsteps; step++) {
             const int rel0 = step * K;
-            if (vbytes > 0) {
+            if (any) {
                 uint32_t a_in = ring_tid + (uint32_t)(slot_in * ring_pitch);
                 uint32_t a_out = ring_tid + (uint32_t)(slot_out * ring_pitch);
                 const int wrap_in = tl.ring_rows - slot_in;            // first k whose entering slot wraps
