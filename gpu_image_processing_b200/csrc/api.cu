@@ -175,13 +175,15 @@ static cudaError_t run_sync(FilterKind kind, const uint8_t* d_in, uint8_t* d_out
 }
 
 // ---- host-buffer path: cached pinned + device staging ---------------------------------------
+constexpr int kMaxChunks = 16;
+
 struct HostCache {
     std::mutex mu;
     int device = -1;
     uint8_t *d_in = nullptr, *d_out = nullptr, *p_in = nullptr, *p_out = nullptr;
     size_t d_cap = 0, p_cap = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;      // upload stream; compute + download stream
+    cudaEvent_t up[kMaxChunks] = {}, k0[kMaxChunks] = {}, k1[kMaxChunks] = {}, down[kMaxChunks] = {};
 
     void release() {
         if (d_in) cudaFree(d_in);
@@ -189,9 +191,15 @@ struct HostCache {
         if (p_in) cudaFreeHost(p_in);
         if (p_out) cudaFreeHost(p_out);
         d_in = d_out = p_in = p_out = nullptr; d_cap = p_cap = 0;
-        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
-        if (e0) { cudaEventDestroy(e0); e0 = nullptr; }
-        if (e1) { cudaEventDestroy(e1); e1 = nullptr; }
+        if (s_in) { cudaStreamDestroy(s_in); s_in = nullptr; }
+        if (s_out) { cudaStreamDestroy(s_out); s_out = nullptr; }
+        for (int i = 0; i < kMaxChunks; i++) {
+            if (up[i]) cudaEventDestroy(up[i]);
+            if (k0[i]) cudaEventDestroy(k0[i]);
+            if (k1[i]) cudaEventDestroy(k1[i]);
+            if (down[i]) cudaEventDestroy(down[i]);
+            up[i] = k0[i] = k1[i] = down[i] = nullptr;
+        }
         device = -1;
     }
     cudaError_t ensure(size_t bytes, bool need_pinned) {
@@ -199,10 +207,15 @@ struct HostCache {
         cudaError_t err = cudaGetDevice(&dev);
         if (err != cudaSuccess) return err;
         if (dev != device) { release(); device = dev; }
-        if (!stream) {
-            if ((err = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return err;
-            if ((err = cudaEventCreate(&e0)) != cudaSuccess) return err;
-            if ((err = cudaEventCreate(&e1)) != cudaSuccess) return err;
+        if (!s_in) {
+            if ((err = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return err;
+            if ((err = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return err;
+            for (int i = 0; i < kMaxChunks; i++) {
+                if ((err = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming)) != cudaSuccess) return err;
+                if ((err = cudaEventCreate(&k0[i])) != cudaSuccess) return err;
+                if ((err = cudaEventCreate(&k1[i])) != cudaSuccess) return err;
+                if ((err = cudaEventCreateWithFlags(&down[i], cudaEventDisableTiming)) != cudaSuccess) return err;
+            }
         }
         if (bytes > d_cap) {
             if (d_in) cudaFree(d_in);
@@ -231,34 +244,86 @@ static bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// bindings.cpp:37-42, :57-63, :77-81 -- H2D, filter, D2H; here with cached buffers, pinned
-// staging (skipped when the caller's memory is already pinned) and a private stream.
+// bindings.cpp:37-42, :57-63, :77-81 -- H2D, filter, D2H.  Here: cached device buffers, pinned staging (skipped
+// when the caller's memory is already pinned), and the transfer is cut into chunks (row bands of one image,
+// or image ranges of a batch) so that the upload of chunk k+1, the kernel of chunk k and the download of
+// chunk k-1 overlap: PCIe runs in both directions at once instead of H2D, kernel, D2H back to back.
 static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out, int64_t width,
                             int64_t height, int channels, int64_t batch, float sigma, int radius,
                             int level, gip_metrics* metrics) {
     if (!level_ok(kind, level)) return cudaErrorNotSupported;
     if (!h_in || !h_out || width <= 0 || height <= 0 || batch <= 0) return cudaErrorInvalidValue;
     if (channels != 1 && channels != 3 && channels != 4) return cudaErrorInvalidValue;
-    const size_t bytes = (size_t)width * height * channels * batch;
+    if (kind != kSobel && radius < 0) return cudaErrorInvalidValue;
+    const int halo = kind == kSobel ? 1 : radius;
+    const int64_t pitch = width * channels;
+    const size_t bytes = (size_t)pitch * height * batch;
     std::lock_guard<std::mutex> lock(g_cache.mu);
     const bool pin_in = is_pinned(h_in), pin_out = is_pinned(h_out);
     cudaError_t err = g_cache.ensure(bytes, !(pin_in && pin_out));
     if (err != cudaSuccess) return err;
-    cudaStream_t s = g_cache.stream;
-    const uint8_t* src = h_in;
-    if (!pin_in) { memcpy(g_cache.p_in, h_in, bytes); src = g_cache.p_in; }
-    uint8_t* dst = pin_out ? h_out : g_cache.p_out;
-    if ((err = cudaMemcpyAsync(g_cache.d_in, src, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return err;
-    cudaEventRecord(g_cache.e0, s);
-    err = enqueue(kind, g_cache.d_in, g_cache.d_out, width, height, channels, batch, sigma, radius, level, nullptr, s);
-    cudaEventRecord(g_cache.e1, s);
-    if (err != cudaSuccess) { cudaStreamSynchronize(s); return err; }
-    if ((err = cudaMemcpyAsync(dst, g_cache.d_out, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return err;
-    if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return err;
-    if (!pin_out) memcpy(h_out, g_cache.p_out, bytes);
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, g_cache.e0, g_cache.e1);
-    fill_metrics(metrics, ms, kind, (int64_t)bytes);
+    HostCache& c = g_cache;
+
+    // chunks: units are rows (one image) or images (a batch); about 8 MB each, at most kMaxChunks
+    const bool by_rows = batch == 1;
+    const int64_t units = by_rows ? height : batch;
+    const int64_t unit_bytes = by_rows ? pitch : pitch * height;
+    int64_t n = (int64_t)(bytes / (8u << 20));
+    if (n > kMaxChunks) n = kMaxChunks;
+    if (n > units) n = units;
+    if (by_rows && halo > 0 && n > 1 && units / n < 4 * (int64_t)halo) n = units / (4 * (int64_t)halo);
+    if (n < 1) n = 1;
+    auto lo_of = [&](int64_t k) { return units * k / n; };
+
+    const uint8_t* src = pin_in ? h_in : c.p_in;
+    uint8_t* dst = pin_out ? h_out : c.p_out;
+    auto compute = [&](int64_t k) -> cudaError_t {           // chunk k: kernel + download, after the uploads it needs
+        const int64_t u0 = lo_of(k), u1 = lo_of(k + 1);
+        cudaStreamWaitEvent(c.s_out, c.up[k + 1 < n ? k + 1 : k], 0);   // halo rows below live in chunk k+1
+        cudaEventRecord(c.k0[k], c.s_out);
+        cudaError_t e;
+        if (by_rows) {
+            BandArgs b;
+            b.y0 = u0; b.rows = u1 - u0;
+            b.rows_above = u0 < halo ? u0 : halo;
+            b.rows_below = (height - u1) < halo ? (height - u1) : halo;
+            b.above = b.rows_above ? c.d_in + (u0 - b.rows_above) * pitch : nullptr;
+            b.below = b.rows_below ? c.d_in + u1 * pitch : nullptr;
+            e = enqueue(kind, c.d_in + u0 * pitch, c.d_out + u0 * pitch, width, height, channels, 1, sigma, radius,
+                        level, n > 1 ? &b : nullptr, c.s_out);
+        } else {
+            e = enqueue(kind, c.d_in + u0 * unit_bytes, c.d_out + u0 * unit_bytes, width, height, channels, u1 - u0,
+                        sigma, radius, level, nullptr, c.s_out);
+        }
+        cudaEventRecord(c.k1[k], c.s_out);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(dst + u0 * unit_bytes, c.d_out + u0 * unit_bytes, (size_t)((u1 - u0) * unit_bytes),
+                            cudaMemcpyDeviceToHost, c.s_out);
+        cudaEventRecord(c.down[k], c.s_out);
+        return e;
+    };
+    for (int64_t k = 0; k < n && err == cudaSuccess; k++) {
+        const int64_t u0 = lo_of(k), u1 = lo_of(k + 1);
+        const size_t off = (size_t)(u0 * unit_bytes), len = (size_t)((u1 - u0) * unit_bytes);
+        if (!pin_in) memcpy(c.p_in + off, h_in + off, len);       // overlaps the DMA of the previous chunk
+        err = cudaMemcpyAsync(c.d_in + off, src + off, len, cudaMemcpyHostToDevice, c.s_in);
+        cudaEventRecord(c.up[k], c.s_in);
+        if (err == cudaSuccess && k >= 1) err = compute(k - 1);
+    }
+    if (err == cudaSuccess) err = compute(n - 1);
+    if (err != cudaSuccess) { cudaStreamSynchronize(c.s_in); cudaStreamSynchronize(c.s_out); return err; }
+    float ms_total = 0.0f;
+    for (int64_t k = 0; k < n; k++) {                              // drain in order: copy out chunk k while k+1 is still in flight
+        if ((err = cudaEventSynchronize(c.down[k])) != cudaSuccess) return err;
+        if (!pin_out) {
+            const size_t off = (size_t)(lo_of(k) * unit_bytes), len = (size_t)((lo_of(k + 1) - lo_of(k)) * unit_bytes);
+            memcpy(h_out + off, c.p_out + off, len);
+        }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, c.k0[k], c.k1[k]);
+        ms_total += ms;
+    }
+    fill_metrics(metrics, ms_total, kind, (int64_t)bytes);
     return cudaSuccess;
 }
 

@@ -141,16 +141,27 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         for (int i = lane; i < sh; i += 32) my_row[i] = 0;
 
         uint32_t head_byte = 0, edge_l = 0, edge_r = 0;
-        auto stage_row = [&](int rel) {                    // rel = row index relative to Ystart
+        // Row pointers advance by K rows inside the band's own memory and are recomputed at the seams (clamped
+        // rows at the image top / bottom, halo rows that live in a neighbour's buffer).
+        const int64_t fast_lo = (job.src.band_y0 > 0 ? job.src.band_y0 : 0) + K;
+        const int64_t fast_hi = job.src.band_y1 < job.height ? job.src.band_y1 : job.height;
+        const int64_t step_bytes = (int64_t)K * pitch;
+        const uint8_t* grow = nullptr;                     // row pointer of the row staged last
+        const bool c0 = 16 * lane < ncopy, c1 = 16 * lane + 512 < ncopy, c2 = 16 * lane + 1024 < ncopy,
+                   c3 = 16 * lane + 1536 < ncopy;
+        const bool has_head = lane < nhead;
+        auto stage_row = [&](int rel) {                    // rel = row index relative to Ystart (this warp: rel = warp mod K)
             if (rel < nrows_in) {
-                const int64_t y = clamp64(Ystart + rel, 0, job.height - 1);
-                const uint8_t* grow = job.src.row(y, img);
+                const int64_t yy = Ystart + rel;
+                if (yy >= fast_lo && yy < fast_hi && grow != nullptr) grow += step_bytes;
+                else grow = job.src.row(clamp64(yy, 0, job.height - 1), img);
                 if (kVec) {
                     const uint8_t* src = grow + lane_off;
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (16 * lane + 512 * i < ncopy) cp_async16(copy_dst + 512 * i, src + 512 * i);
-                    if (lane < nhead) head_byte = grow[lo + lane];
+                    if (c0) cp_async16(copy_dst, src);
+                    if (c1) cp_async16(copy_dst + 512, src + 512);
+                    if (c2) cp_async16(copy_dst + 1024, src + 1024);
+                    if (c3) cp_async16(copy_dst + 1536, src + 1536);
+                    if (has_head) head_byte = grow[lo + lane];
                 } else {
                     const uint8_t* src = grow + cs;
                     for (int o = lane; o < ncopy; o += 32) copy_dst_g[o] = src[o];
@@ -181,7 +192,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             const int rel0 = step * K;
             if (rel0 + warp < nrows_in) {
                 cp_async_wait<0>();
-                if (kVec && lane < nhead) my_row[head_idx + lane] = (uint8_t)head_byte;
+                if (kVec && has_head) my_row[head_idx + lane] = (uint8_t)head_byte;
                 if (nleft > 0)         // left image edge: replicate pixel 0
                     for (int i = lane; i < nleft; i += 32) my_row[sh + i] = (uint8_t)(edge_l >> (8 * (i % C)));
                 if (nright > 0)        // right image edge: replicate the last pixel
@@ -220,17 +231,34 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                         acc[ch] = dp4a_us(k < 2 ? pa : pb, (k & 1) ? (int)0xFF010000 : 0x0000FF01, acc[ch]);
                     }
                 }
-                // exclusive scan over lanes -> window sum at the byte before this lane's run (as 2^23 + sum)
-#pragma unroll
-                for (int c = 0; c < ((C == 1) ? 1 : NACC); c++) {
-                    const int t = acc[c];
-                    int x = t;
+                // exclusive scan over lanes -> window sum at the byte before this lane's run (as 2^23 + sum).
+                // Window sums and lane totals are below 2^15 in magnitude, so two channels share one register
+                // (lo + 65536 * hi in two's complement) and the SHFL scan runs on half as many registers.
+                auto scan_incl = [&](int x) {
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const int v = __shfl_up_sync(0xffffffffu, x, d);
                         if (lane >= d) x += v;
                     }
-                    acc[c] = x - t + (int)kBias;
+                    return x;
+                };
+                if (C == 1) {
+                    acc[0] = scan_incl(acc[0]) - acc[0] + (int)kBias;
+                } else {
+                    const int p01 = acc[0] + acc[1] * 65536;
+                    const int e01 = scan_incl(p01) - p01;                    // exclusive, still packed
+                    const int b0 = (int)(short)(e01 & 0xFFFF);
+                    acc[0] = b0 + (int)kBias;
+                    acc[1] = ((e01 - b0) >> 16) + (int)kBias;
+                    if (C == 3) {
+                        acc[2] = scan_incl(acc[2]) - acc[2] + (int)kBias;
+                    } else {
+                        const int p23 = acc[2] + acc[3 % NACC] * 65536;
+                        const int e23 = scan_incl(p23) - p23;
+                        const int b2 = (int)(short)(e23 & 0xFFFF);
+                        acc[2] = b2 + (int)kBias;
+                        acc[3 % NACC] = ((e23 - b2) >> 16) + (int)kBias;
+                    }
                 }
                 // phase B: replay the recurrence from the true start value, round, store to the ring
                 if (lane >= tl.nw) {
