@@ -121,14 +121,18 @@ def cpu_port_run(steps, warmup, rows=1024):
     from oracle import oracle as O
     from tests import synth
     img = synth.uniform(rows, W, C, seed=1234)
-    cores = O.max_threads()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the scheduler instead)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     for _ in range(max(0, min(warmup, 1))):
-        O.box_blur(img, 3)
+        O.box_blur(img, 3, nthreads=cores)
     times = []
     for _ in range(max(1, steps)):
         t0 = time.perf_counter()
         for r in RADII:
-            O.box_blur(img, r)
+            O.box_blur(img, r, nthreads=cores)
         times.append(time.perf_counter() - t0)
     best = min(times)
     mpix = rows * W * len(RADII) / best / 1e6
