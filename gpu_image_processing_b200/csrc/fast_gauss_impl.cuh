@@ -86,11 +86,12 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         }
         cp_async_commit();
         cp_async_wait<0>();
-    } else {
+    } else {               // rows that are not 4-byte aligned: a warp per row, plain byte copies
         const int n = hi > lo ? (int)(hi - lo) : 0;
-        for (int idx = tid; idx < n * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / n, i = idx - rr * n;
-            in_tile[rr * in_pitch + (int)(lo - b0) + i] = job.src.row(row0 + rr, img)[lo + i];
+        for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
+            const uint8_t* src = job.src.row(row0 + rr, img) + lo;
+            uint8_t* dst = in_tile + rr * in_pitch + (int)(lo - b0);
+            for (int i = lane; i < n; i += 32) dst[i] = src[i];
         }
     }
     __syncthreads();

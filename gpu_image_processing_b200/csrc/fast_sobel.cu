@@ -127,7 +127,7 @@ __device__ __forceinline__ uint64_t sobel_pair(uint64_t TL, uint64_t TC, uint64_
 __device__ __forceinline__ uint32_t clamp255(uint32_t z) { return min(z, 0x4B0000FFu); }
 
 template <int C, bool kU8, bool kVec16>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTiling tl) {
     const int lane = threadIdx.x & 31;
     long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -210,25 +210,28 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
         out += pitch;
     };
 
-    // rows Y0-1 and Y0 prime the pipeline; the words of the next row are always in flight
+    // rows Y0-1 and Y0 prime the pipeline; the words of the next THREE rows are always in flight (three word
+    // buffers rotate with the three gray rows, so nothing is copied between iterations)
     rp_y = Y0 - 3;
     GrayRow R0 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0 - 1), off), lane);
     GrayRow R1 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0), off), lane);
     GrayRow R2;
-    RowWords<C> nxt = load_words<C, kVec16>(next_row(Y0 + 1), off);
+    RowWords<C> W0 = load_words<C, kVec16>(next_row(Y0 + 1), off);
+    RowWords<C> W1 = load_words<C, kVec16>(next_row(Y0 + 2), off);
+    RowWords<C> W2 = load_words<C, kVec16>(next_row(Y0 + 3), off);
     for (int i = 0; i < nrows; i += 3) {
         const int y = y_first + i;
-        // output row y needs rows y-1 (R0), y (R1), y+1 (nxt -> R2)
-        R2 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(next_row((int64_t)y + 2), off);
+        // output row y needs rows y-1 (R0), y (R1), y+1 (W0 -> R2)
+        R2 = make_gray<C, kU8>(W0, lane);
+        W0 = load_words<C, kVec16>(next_row((int64_t)y + 4), off);
         emit(R0, R1, R2, y);
         if (i + 1 >= nrows) break;
-        R0 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(next_row((int64_t)y + 3), off);
+        R0 = make_gray<C, kU8>(W1, lane);
+        W1 = load_words<C, kVec16>(next_row((int64_t)y + 5), off);
         emit(R1, R2, R0, y + 1);
         if (i + 2 >= nrows) break;
-        R1 = make_gray<C, kU8>(nxt, lane);
-        nxt = load_words<C, kVec16>(next_row((int64_t)y + 4), off);
+        R1 = make_gray<C, kU8>(W2, lane);
+        W2 = load_words<C, kVec16>(next_row((int64_t)y + 6), off);
         emit(R2, R0, R1, y + 2);
     }
 }
