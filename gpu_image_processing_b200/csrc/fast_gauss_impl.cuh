@@ -99,11 +99,12 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         const int nl = b0 < 0 ? (int)(-b0) : 0;
         const int nr = (b0 + tile_bytes > pitch) ? (int)(b0 + tile_bytes - pitch) : 0;
         const int first_r = tile_bytes - nr;
-        for (int idx = tid; idx < (nl + nr) * nrows; idx += HCfg<C>::kThreads) {
-            const int rr = idx / (nl + nr), i = idx - rr * (nl + nr);
-            uint8_t* rowp = in_tile + rr * in_pitch + skew;
-            if (i < nl) rowp[i] = rowp[nl + (i % C)];                                   // b0 is a multiple of C
-            else { const int k = i - nl; rowp[first_r + k] = rowp[first_r - C + (k % C)]; }
+        if (nl + nr > 0) {
+            for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
+                uint8_t* rowp = in_tile + rr * in_pitch + skew;
+                for (int i = lane; i < nl; i += 32) rowp[i] = rowp[nl + (i % C)];                 // b0 is a multiple of C
+                for (int k = lane; k < nr; k += 32) rowp[first_r + k] = rowp[first_r - C + (k % C)];
+            }
         }
     }
     __syncthreads();
@@ -155,10 +156,10 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     int64_t out_bytes = (int64_t)TW * C; if (ob0 + out_bytes > pitch) out_bytes = pitch - ob0;
     uint8_t* tbase = tmp + ((img - img0) * (ty1 - ty0) + (row0 - ty0)) * tpitch + ob0;
     const int nv = (int)((out_bytes + 3) >> 2);
-    for (int idx = tid; idx < nv * nrows; idx += HCfg<C>::kThreads) {
-        const int rr = idx / nv, ci = idx - rr * nv;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(out_tile + rr * out_pitch + 4 * ci);
-        *reinterpret_cast<uint32_t*>(tbase + (int64_t)rr * tpitch + 4 * ci) = v;
+    for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {      // a warp per row: coalesced, no index division
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(out_tile + rr * out_pitch);
+        uint32_t* grow = reinterpret_cast<uint32_t*>(tbase + (int64_t)rr * tpitch);
+        for (int ci = lane; ci < nv; ci += 32) grow[ci] = srow[ci];
     }
 }
 
@@ -189,9 +190,14 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
     const int nsteps = (int)(Y1 - Y0) + 2 * R;                    // input rows Y0-R .. Y1-1+R (clamped to the image)
     constexpr int M = (8 + R2 - 1) / R2;                          // blocks per super-block: >= 8 rows of loads in flight
     constexpr int U = M * R2;
+    // input row of step s is clamp(Y0 - R + s, 0, H - 1): clamp the step index instead (32-bit), one IMAD.WIDE per load
+    const int s_lo = (Y0 - R < 0) ? (int)(R - Y0) : 0;
+    const int s_hi_img = (int)(H - 1 - (Y0 - R));
+    const int s_hi = s_hi_img < nsteps - 1 ? s_hi_img : nsteps - 1;
+    const uint8_t* tbase0 = timg + (Y0 - R - ty0) * tpitch;         // row of step 0 (may lie above the image: never dereferenced unclamped)
     auto load = [&](int s) {
-        const int64_t y = clamp64(Y0 - R + (s < nsteps ? s : nsteps - 1), 0, H - 1);
-        return __ldg(reinterpret_cast<const uint32_t*>(timg + (y - ty0) * tpitch));
+        const int sc = s < s_lo ? s_lo : (s > s_hi ? s_hi : s);
+        return __ldg(reinterpret_cast<const uint32_t*>(tbase0 + (int64_t)sc * tpitch));
     };
 #define GIP_V_STEP(WORD, U_, EMIT)                                                                       \
     {                                                                                                    \
