@@ -213,3 +213,59 @@ def test_baseline_config_shapes_against_oracle_bands():
         n = 48
         _check(kind, fast[:n], top(img[:n + r])[:n], f"{kind} top rows")
         _check(kind, fast[-n:], top(img[-(n + r):])[-n:], f"{kind} bottom rows")
+
+
+def test_gigapixel_c5_gaussian_64bit_indexing():
+    """BASELINE config c5 at full size: 32768 x 32768 RGB (3.2 GB > 2^31 bytes, which the reference's int
+    arithmetic cannot address, image_filters.cu:95,:760), Gaussian sigma=5 radius=15.  Properties: the fused
+    path equals the general path on the whole image; the oracle reproduces a band at the top edge, one that
+    straddles the 2^31-byte offset, and one at the bottom edge."""
+    import torch
+    from gpu_image_processing_b200 import device
+    L = _lib.load()
+    H = W = 32768
+    C, r, sigma = 3, 15, 5.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 14 * 2 ** 30:
+        pytest.skip("needs ~13 GB of device memory")
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randint(0, 256, (H, W, C), dtype=torch.uint8, device="cuda", generator=g)
+    fast = device.gaussian_blur(x, sigma, r, 2)
+    old = L.gip_set_path(1)
+    try:
+        general = device.gaussian_blur(x, sigma, r, 2)
+    finally:
+        L.gip_set_path(old)
+    assert torch.equal(fast, general)
+    del general
+    y_2g = (2 ** 31) // (W * C)                      # the row that contains byte offset 2^31
+    for y0, y1 in ((0, 24), (y_2g - 12, y_2g + 12), (H - 24, H)):
+        a, b = max(0, y0 - r), min(H, y1 + r)
+        sub = x[a:b].cpu().numpy()
+        want = O.gaussian_blur(sub, sigma, r)[y0 - a:y0 - a + (y1 - y0)]
+        _check("gaussian", fast[y0:y1].cpu().numpy(), want, f"c5 rows {y0}:{y1}")
+
+
+def test_frame_stream_c4_subset():
+    """BASELINE config c4: 1920x1080 RGB frames, all three filters, one batched launch per filter; a 96-frame
+    slice of the 4096-frame stream, every 16th frame against the oracle, fast path == general path on all."""
+    import torch
+    from gpu_image_processing_b200 import device
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randint(0, 256, (96, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    runs = {"gaussian": lambda: device.gaussian_blur(x, 2.0, 3, 2), "box": lambda: device.box_blur(x, 3, 2),
+            "sobel": lambda: device.sobel_edge_detection(x, 1)}
+    for kind, run in runs.items():
+        fast = run()
+        old = L.gip_set_path(1)
+        try:
+            general = run()
+        finally:
+            L.gip_set_path(old)
+        assert torch.equal(fast, general), kind
+        for i in range(0, 96, 16):
+            f = x[i].cpu().numpy()
+            want = {"gaussian": lambda: O.gaussian_blur(f, 2.0, 3), "box": lambda: O.box_blur(f, 3),
+                    "sobel": lambda: O.sobel(f, 1)}[kind]()
+            _check(kind, fast[i].cpu().numpy(), want, f"c4 frame {i} {kind}")
