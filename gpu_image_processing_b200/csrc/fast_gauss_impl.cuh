@@ -29,11 +29,14 @@ namespace {
 
 constexpr int kMaxFastRadius = 15;
 constexpr int kTileRows = 64;           // H pass: 32 row pairs (rows l and l+32 are one lane's pair)
-constexpr int kSegPixels = 128;         // H pass: pixels per thread segment
+constexpr int kTileBytesMax = 1024;     // H pass: tile width in bytes (256 RGBA / 256 RGB / 1024 gray pixels)
 
-template <int C> struct HCfg {
-    static constexpr int kSegs = (C == 1) ? 8 : 2;
-    static constexpr int kTilePixels = kSegs * kSegPixels;
+// A thread marches over a segment of kSegPixels pixels (+ 2R of warm-up).  Short segments for small radii double
+// the number of warps per tile (occupancy) at a warm-up overhead of 2R / kSegPixels.
+template <int C, int R> struct HCfg {
+    static constexpr int kSegPixels = (R <= 4) ? 64 : 128;
+    static constexpr int kTilePixels = (C == 1) ? 1024 : 256;
+    static constexpr int kSegs = kTilePixels / kSegPixels;
     static constexpr int kThreads = 32 * C * kSegs;
 };
 
@@ -49,12 +52,13 @@ __device__ __forceinline__ uint64_t round_pair(uint64_t acc) {
 // H pass.  Image rows [ty0, ty1) of every image of the chunk -> scratch image `tmp` (same pitch).
 // ------------------------------------------------------------------------------------------------
 template <int R, int C, bool kVec>
-__global__ void __launch_bounds__(HCfg<C>::kThreads, 1)
+__global__ void __launch_bounds__(HCfg<C, R>::kThreads, 1)
 gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int tiles_x, int tiles_y, int in_pitch, int out_pitch, int64_t tpitch) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int R2 = 2 * R + 1;
-    constexpr int TW = HCfg<C>::kTilePixels;
+    constexpr int TW = HCfg<C, R>::kTilePixels;
+    constexpr int kSegPixels = HCfg<C, R>::kSegPixels;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t W = job.width, pitch = job.src.pitch;
     unsigned t = blockIdx.x;
@@ -79,7 +83,7 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         int64_t ce = (hi + 3) & ~int64_t(3); if (ce > pitch) ce = pitch;
         const int nchunk = ce > cs ? (int)((ce - cs) >> 2) : 0;
         const uint32_t in_s = smem_addr(in_tile);
-        for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
+        for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
             const uint8_t* src = job.src.row(row0 + rr, img) + cs;
             const uint32_t dst = in_s + (uint32_t)(rr * in_pitch + skew + (int)(cs - b0));
             for (int ci = lane; ci < nchunk; ci += 32) cp_async4(dst + 4 * ci, src + 4 * ci);
@@ -88,7 +92,7 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         cp_async_wait<0>();
     } else {               // rows that are not 4-byte aligned: a warp per row, plain byte copies
         const int n = hi > lo ? (int)(hi - lo) : 0;
-        for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
+        for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
             const uint8_t* src = job.src.row(row0 + rr, img) + lo;
             uint8_t* dst = in_tile + rr * in_pitch + (int)(lo - b0);
             for (int i = lane; i < n; i += 32) dst[i] = src[i];
@@ -100,7 +104,7 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         const int nr = (b0 + tile_bytes > pitch) ? (int)(b0 + tile_bytes - pitch) : 0;
         const int first_r = tile_bytes - nr;
         if (nl + nr > 0) {
-            for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {
+            for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
                 uint8_t* rowp = in_tile + rr * in_pitch + skew;
                 for (int i = lane; i < nl; i += 32) rowp[i] = rowp[nl + (i % C)];                 // b0 is a multiple of C
                 for (int k = lane; k < nr; k += 32) rowp[first_r + k] = rowp[first_r - C + (k % C)];
@@ -156,7 +160,7 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     int64_t out_bytes = (int64_t)TW * C; if (ob0 + out_bytes > pitch) out_bytes = pitch - ob0;
     uint8_t* tbase = tmp + ((img - img0) * (ty1 - ty0) + (row0 - ty0)) * tpitch + ob0;
     const int nv = (int)((out_bytes + 3) >> 2);
-    for (int rr = warp; rr < nrows; rr += HCfg<C>::kThreads / 32) {      // a warp per row: coalesced, no index division
+    for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {      // a warp per row: coalesced, no index division
         const uint32_t* srow = reinterpret_cast<const uint32_t*>(out_tile + rr * out_pitch);
         uint32_t* grow = reinterpret_cast<uint32_t*>(tbase + (int64_t)rr * tpitch);
         for (int ci = lane; ci < nv; ci += 32) grow[ci] = srow[ci];
@@ -242,7 +246,7 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
 template <int R, int C>
 cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, int64_t ty1, int64_t img0, int64_t nimg,
                      bool vec, cudaStream_t stream) {
-    constexpr int TW = HCfg<C>::kTilePixels;
+    constexpr int TW = HCfg<C, R>::kTilePixels;
     const int tiles_x = (int)((job.width + TW - 1) / TW);
     const int tiles_y = (int)((ty1 - ty0 + kTileRows - 1) / kTileRows);
     int in_pitch = ((TW + 2 * R) * C + 32 + 3) & ~3;            // + skew and chunk-rounding room, whole words
@@ -256,11 +260,11 @@ cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, 
     if (vec) {
         static bool set = false;
         if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, true><<<(unsigned)blocks, HCfg<C>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
+        gip_gauss_h<R, C, true><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
     } else {
         static bool set = false;
         if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, false><<<(unsigned)blocks, HCfg<C>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
+        gip_gauss_h<R, C, false><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
     }
     count_launch();
     return cudaGetLastError();
