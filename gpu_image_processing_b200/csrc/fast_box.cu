@@ -8,7 +8,7 @@
 // horizontal box tap at pixel offset i is byte offset C*i, so the H pass is the same code for
 // C = 1, 3, 4.  A CTA owns a column strip of `useful` output bytes and a band of rows and
 // marches down the band K = 10 rows at a time.  The CTA is warp-specialised: 10 producer warps
-// (stage + H pass, one row each) run one step ahead of 5 consumer warps (V pass + store); one
+// (stage + H pass, one row each) run one step ahead of 4 consumer warps (V pass + store); one
 // __syncthreads per step hands a step's rows over.  64 registers per thread: two CTAs per SM.
 //   stage   producer warp w copies input row w of the step (strip + halo) into its private
 //           shared-memory row with 16-byte cp.async (LDGSTS), issued as soon as the previous row
@@ -22,7 +22,7 @@
 //           window fills without a separate O(radius) initial sum: cost is independent of radius.
 //           The rounded average (the reference's u8 intermediate, :394) goes to a ring of
 //           2r+1+2K u8 rows in shared memory.
-//   V pass  one thread per 12-byte column group keeps its twelve window sums in registers across
+//   V pass  one thread per 16-byte column group keeps its sixteen window sums in registers across
 //           the whole band: add the entering ring row, subtract the leaving one (IDP.4A), round,
 //           store.  The intermediate never leaves the SM.
 // Rounding.  The reference computes (uchar)(S*(1.0f/k)+0.5f) (:394, :429), which equals
@@ -40,11 +40,11 @@ constexpr int kLaneWords = 15;
 constexpr int kLaneBytes = 4 * kLaneWords;      // 60
 constexpr int kWarpRun = 32 * kLaneBytes;       // 1920 bytes of recurrence per staged row
 constexpr int kHWarps = 10;                     // producer warps: one staged row each per step
-constexpr int kVWarps = 5;                      // consumer warps: 160 threads x 12-byte column groups >= 1860 bytes
+constexpr int kVWarps = 4;                      // consumer warps: 128 threads x 16-byte column groups >= 1856 bytes
 constexpr int kWarps = kHWarps + kVWarps;
-constexpr int kThreads = 32 * kWarps;           // 480
+constexpr int kThreads = 32 * kWarps;           // 448
 constexpr int K = kHWarps;                      // rows per step
-constexpr int kGroupBytes = 12;                 // V-pass column group (60 = 5 x 12)
+constexpr int kGroupBytes = 16;                 // V-pass column group: one LDS.128 / STG.128
 constexpr uint32_t kBias = 0x4B000000u;         // float 2^23
 constexpr int kSmemLimit = 225 * 1024;
 constexpr int kSmemTwoPerSM = 113 * 1024;
@@ -56,7 +56,8 @@ __constant__ BoxMagic c_box_magic[32] = {
 
 struct BoxTiling {
     int nw;              // warm-up lanes = ceil((2r+1)*C / 60)
-    int useful;          // output bytes per strip = (32 - nw) * 60
+    int useful;          // output bytes per strip = (32 - nw) * 60 rounded down to a multiple of 16
+    int ring_pitch;      // bytes per ring row = (32 - nw) * 60 rounded up to a multiple of 16
     int strips;          // strips per row
     int bands;           // row bands per image
     int band_rows;       // rows per band
@@ -100,7 +101,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
     const int64_t e0 = bxs - (int64_t)kLaneBytes * tl.nw + (int64_t)r * C;   // image-row position of buffer index sh
     const int64_t B0 = e0 - sh;                      // image-row byte position of buffer index 0
     const uint32_t ring_s = smem_addr(smem + (size_t)K * tl.stage_row);
-    const int ring_pitch = tl.useful;
+    const int ring_pitch = tl.ring_pitch;
     const int ring_bytes = tl.ring_rows * ring_pitch;
     const uint32_t mag_a = c_box_magic[r].a_bits, mag_c = c_box_magic[r].c_bits;
     const uint64_t mag_a2 = pack_f2(mag_a, mag_a), mag_c2 = pack_f2(mag_c, mag_c);
@@ -285,34 +286,30 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         __syncthreads();          // matches the consumers' last barrier
     } else {
         // ==================================== consumer warp ====================================
-        // Thread vt owns the 4-byte column groups vt, vt + nvt, vt + 2 nvt of the strip (nvt = useful / 12): every
-        // LDS.32 / STG.32 of a warp then covers 32 consecutive words (full 128-byte lines, no partial sectors).
+        // Thread vt owns the 16-byte column group vt of the strip: one LDS.128 per ring row, one STG.128 per output row,
+        // a warp covers 512 contiguous bytes.
         const int vt = tid - 32 * kHWarps;
         const int nvt = tl.useful / kGroupBytes;
-        int vbytes[3];
-        bool any = false;
-#pragma unroll
-        for (int w = 0; w < 3; w++) {
-            const int64_t c = bxs + 4 * (int64_t)(vt + w * nvt);
-            vbytes[w] = (vt < nvt && c < pitch) ? ((pitch - c >= 4) ? 4 : (int)(pitch - c)) : 0;
-            any |= vbytes[w] > 0;
-        }
+        const int64_t col = bxs + (int64_t)kGroupBytes * vt;
+        int vbytes = 0;
+        if (vt < nvt && col < pitch) vbytes = (pitch - col >= kGroupBytes) ? kGroupBytes : (int)(pitch - col);
+        const bool any = vbytes > 0;
         uint32_t S[kGroupBytes];
 #pragma unroll
         for (int i = 0; i < kGroupBytes; i++) S[i] = kBias;
-        const int wstride = 4 * nvt;                     // bytes between this thread's column groups
-        uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + bxs + 4 * (int64_t)vt;  // next output row
-        const uint32_t ring_tid = ring_s + 4u * (uint32_t)(vt < nvt ? vt : 0);
+        uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;  // next output row
+        const uint32_t ring_tid = ring_s + (uint32_t)(kGroupBytes * (vt < nvt ? vt : 0));
 
         auto v_row = [&](uint32_t a_in, uint32_t a_out, bool leave, bool store) {
-            uint32_t res[3];
+            const uint4 in4 = lds128(a_in);
+            uint4 out4 = make_uint4(0u, 0u, 0u, 0u);
+            if (leave) out4 = lds128(a_out);
+            const uint32_t iw[4] = {in4.x, in4.y, in4.z, in4.w}, ow[4] = {out4.x, out4.y, out4.z, out4.w};
+            uint32_t res[4];
 #pragma unroll
-            for (int w = 0; w < 3; w++) {
-                const uint32_t iw = lds32(a_in + w * wstride);
-                uint32_t ow = 0;
-                if (leave) ow = lds32(a_out + w * wstride);
-                const uint32_t pa = __byte_perm(iw, ow, 0x5140);
-                const uint32_t pb = __byte_perm(iw, ow, 0x7362);
+            for (int w = 0; w < 4; w++) {
+                const uint32_t pa = __byte_perm(iw[w], ow[w], 0x5140);
+                const uint32_t pb = __byte_perm(iw[w], ow[w], 0x7362);
                 S[4 * w + 0] = (uint32_t)dp4a_us(pa, 0x0000FF01, (int)S[4 * w + 0]);
                 S[4 * w + 1] = (uint32_t)dp4a_us(pa, (int)0xFF010000, (int)S[4 * w + 1]);
                 S[4 * w + 2] = (uint32_t)dp4a_us(pb, 0x0000FF01, (int)S[4 * w + 2]);
@@ -320,13 +317,10 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                 if (store) res[w] = round_pack(S[4 * w], S[4 * w + 1], S[4 * w + 2], S[4 * w + 3], mag_a2, mag_c2);
             }
             if (store) {
-#pragma unroll
-                for (int w = 0; w < 3; w++) {
-                    if (kVec) {
-                        if (vbytes[w]) stg32_stream(optr + w * wstride, res[w]);
-                    } else {
-                        for (int b = 0; b < vbytes[w]; b++) optr[w * wstride + b] = (uint8_t)(res[w] >> (8 * b));
-                    }
+                if (kVec) {
+                    stg128_stream(optr, make_uint4(res[0], res[1], res[2], res[3]));
+                } else {
+                    for (int b = 0; b < vbytes; b++) optr[b] = (uint8_t)(res[b >> 2] >> (8 * (b & 3)));
                 }
                 optr += pitch;
             }
@@ -402,12 +396,13 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     BoxTiling tl;
     const int sh = (2 * r + 1) * C;
     tl.nw = (sh + kLaneBytes - 1) / kLaneBytes;
-    tl.useful = (32 - tl.nw) * kLaneBytes;
+    tl.useful = ((32 - tl.nw) * kLaneBytes) & ~15;
+    tl.ring_pitch = ((32 - tl.nw) * kLaneBytes + 15) & ~15;
     const int64_t pitch = job.src.pitch;
     tl.strips = (int)((pitch + tl.useful - 1) / tl.useful);
     tl.ring_rows = 2 * r + 1 + 2 * K;
     tl.stage_row = (sh + kWarpRun + 31 + 15) & ~15;
-    const size_t smem = (size_t)K * tl.stage_row + (size_t)tl.ring_rows * tl.useful;
+    const size_t smem = (size_t)K * tl.stage_row + (size_t)tl.ring_rows * tl.ring_pitch;
     if (smem > (size_t)kSmemLimit) return cudaSuccess;
     const int ctas_per_sm = smem <= (size_t)kSmemTwoPerSM ? 2 : 1;
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
@@ -430,7 +425,7 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     const int64_t tiles = per_band * tl.bands;
     if (tiles > 0x7fffffff) return cudaSuccess;      // general path
     const bool vec = (pitch % 16 == 0) && (job.src.image_stride % 16 == 0) &&
-                     ((uintptr_t)job.src.band % 16 == 0) && ((uintptr_t)job.out % 4 == 0) &&
+                     ((uintptr_t)job.src.band % 16 == 0) && ((uintptr_t)job.out % 16 == 0) &&
                      (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
                      (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
     cudaError_t err;
