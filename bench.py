@@ -157,7 +157,7 @@ def run_reference_arm(args):
             "gpu_launches": 0,
             "note": "reference arm = CPU port of the reference's level-1 math on the host cores; each step is the "
                     "bounded sample named in cpu_baseline.sample"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -335,12 +335,31 @@ def main():
             line["cpu_baseline"], _ = cpu_port_run(1, 1)
             line["reference_cuda_same_gpu"] = reference_cuda_same_gpu(torch, xs[0], ys[0])
             line["filters"] = other_configs(torch, device)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Keep stdout for the one JSON line: libraries (NCCL's version banner, the reference's printf) write to fd 1,
+    so point fd 1 at stderr for the run and keep a private duplicate of the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    quiet_stdout()
     sys.exit(main())

@@ -2,11 +2,15 @@
 // (include/image_filters.h) on top of the kernels.  Validation, job construction, dispatch
 // between the fused fast path and the general path, CUDA-event timing, host-buffer staging.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/gip_b200.h"
 #include "../../include/image_filters.h"
@@ -175,15 +179,21 @@ static cudaError_t run_sync(FilterKind kind, const uint8_t* d_in, uint8_t* d_out
 }
 
 // ---- host-buffer path: cached pinned + device staging ---------------------------------------
-constexpr int kMaxChunks = 16;
+constexpr int kMaxChunks = 32;
 
+static long env_long(const char* name, long fallback) {
+    const char* e = getenv(name);
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? v : fallback;
+}
 struct HostCache {
     std::mutex mu;
     int device = -1;
     uint8_t *d_in = nullptr, *d_out = nullptr, *p_in = nullptr, *p_out = nullptr;
     size_t d_cap = 0, p_cap = 0;
-    cudaStream_t s_in = nullptr, s_out = nullptr;      // upload stream; compute + download stream
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;      // upload, kernels, download
     cudaEvent_t up[kMaxChunks] = {}, k0[kMaxChunks] = {}, k1[kMaxChunks] = {}, down[kMaxChunks] = {};
+    cudaEvent_t t0 = nullptr;                                          // start of the call on s_in (GIP_VERBOSE trace)
 
     void release() {
         if (d_in) cudaFree(d_in);
@@ -191,31 +201,31 @@ struct HostCache {
         if (p_in) cudaFreeHost(p_in);
         if (p_out) cudaFreeHost(p_out);
         d_in = d_out = p_in = p_out = nullptr; d_cap = p_cap = 0;
-        if (s_in) { cudaStreamDestroy(s_in); s_in = nullptr; }
-        if (s_out) { cudaStreamDestroy(s_out); s_out = nullptr; }
+        for (cudaStream_t* s : {&s_in, &s_k, &s_out})
+            if (*s) { cudaStreamDestroy(*s); *s = nullptr; }
         for (int i = 0; i < kMaxChunks; i++) {
-            if (up[i]) cudaEventDestroy(up[i]);
-            if (k0[i]) cudaEventDestroy(k0[i]);
-            if (k1[i]) cudaEventDestroy(k1[i]);
-            if (down[i]) cudaEventDestroy(down[i]);
-            up[i] = k0[i] = k1[i] = down[i] = nullptr;
+            for (cudaEvent_t* e : {&up[i], &k0[i], &k1[i], &down[i]})
+                if (*e) { cudaEventDestroy(*e); *e = nullptr; }
         }
+        if (t0) { cudaEventDestroy(t0); t0 = nullptr; }
         device = -1;
     }
-    cudaError_t ensure(size_t bytes, bool need_pinned) {
+    cudaError_t ensure(size_t bytes, bool pinned_in, bool pinned_out) {
         int dev = 0;
         cudaError_t err = cudaGetDevice(&dev);
         if (err != cudaSuccess) return err;
         if (dev != device) { release(); device = dev; }
-        if (!s_in) {
-            if ((err = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return err;
-            if ((err = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return err;
+        if (!s_out) {
+            for (cudaStream_t* s : {&s_in, &s_k, &s_out})
+                if (!*s && (err = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return err;
+            const unsigned flags = verbose() ? cudaEventDefault : cudaEventDisableTiming;
             for (int i = 0; i < kMaxChunks; i++) {
-                if ((err = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming)) != cudaSuccess) return err;
-                if ((err = cudaEventCreate(&k0[i])) != cudaSuccess) return err;
-                if ((err = cudaEventCreate(&k1[i])) != cudaSuccess) return err;
-                if ((err = cudaEventCreateWithFlags(&down[i], cudaEventDisableTiming)) != cudaSuccess) return err;
+                if (!up[i] && (err = cudaEventCreateWithFlags(&up[i], flags)) != cudaSuccess) return err;
+                if (!k0[i] && (err = cudaEventCreate(&k0[i])) != cudaSuccess) return err;
+                if (!k1[i] && (err = cudaEventCreate(&k1[i])) != cudaSuccess) return err;
+                if (!down[i] && (err = cudaEventCreateWithFlags(&down[i], flags)) != cudaSuccess) return err;
             }
+            if (!t0 && (err = cudaEventCreate(&t0)) != cudaSuccess) return err;
         }
         if (bytes > d_cap) {
             if (d_in) cudaFree(d_in);
@@ -225,7 +235,7 @@ struct HostCache {
             if ((err = cudaMalloc((void**)&d_out, bytes)) != cudaSuccess) return err;
             d_cap = bytes;
         }
-        if (need_pinned && bytes > p_cap) {
+        if ((pinned_in || pinned_out) && bytes > p_cap) {
             if (p_in) cudaFreeHost(p_in);
             if (p_out) cudaFreeHost(p_out);
             p_in = p_out = nullptr; p_cap = 0;
@@ -238,16 +248,97 @@ struct HostCache {
 };
 static HostCache g_cache;
 
+// Target chunk size of the host pipeline (GIP_HOST_CHUNK_KB, default 4 MB) and the number of helper threads that
+// copy between pageable caller memory and the pinned staging buffers (GIP_HOST_THREADS, default 4: half stage the
+// input, half drain the output).  Tuning knobs; the defaults are what bench.py / the tests run.
+static size_t host_chunk_bytes() {
+    static const size_t v = (size_t)env_long("GIP_HOST_CHUNK_KB", 4096) << 10;
+    return v;
+}
+static int host_threads() {
+    static const int v = (int)env_long("GIP_HOST_THREADS", 4);
+    return v < 2 ? 2 : (v > 16 ? 16 : v);
+}
+
 static bool is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
 
+// One host call, cut into chunks (row bands of one image, or image ranges of a batch).
+struct HostPlan {
+    FilterKind kind; int64_t width, height; int channels; int64_t batch; float sigma; int radius, level;
+    bool by_rows; int halo; int64_t pitch, units, unit_bytes, n;
+    const uint8_t* src; uint8_t* dst;          // pinned: the caller's own memory or the staging buffers
+    int64_t lo(int64_t k) const { return units * k / n; }
+    size_t off(int64_t k) const { return (size_t)(lo(k) * unit_bytes); }
+    size_t len(int64_t k) const { return (size_t)((lo(k + 1) - lo(k)) * unit_bytes); }
+};
+
+static cudaError_t issue_upload(const HostPlan& p, HostCache& c, int64_t k) {
+    cudaError_t e = cudaMemcpyAsync(c.d_in + p.off(k), p.src + p.off(k), p.len(k), cudaMemcpyHostToDevice, c.s_in);
+    cudaEventRecord(c.up[k], c.s_in);
+    return e;
+}
+
+// chunk k: kernel on s_k once the uploads it reads are done, download on s_out once the kernel is done.
+// Three streams, so the download of chunk k-1 runs under the kernel of chunk k and under the upload of k+2.
+// (Measured alternatives, tools/zero_copy.py: kernels storing straight into the pinned output reach the DMA's
+// 51 GB/s only as one whole-image launch; as per-chunk band launches they are slower than this staged form.)
+static cudaError_t issue_compute(const HostPlan& p, HostCache& c, int64_t k) {
+    const int64_t u0 = p.lo(k), u1 = p.lo(k + 1);
+    uint8_t* const out_base = c.d_out;
+    cudaStreamWaitEvent(c.s_k, c.up[k + 1 < p.n ? k + 1 : k], 0);   // the halo rows below live in chunk k+1
+    cudaEventRecord(c.k0[k], c.s_k);
+    cudaError_t e;
+    if (p.by_rows) {
+        BandArgs b;
+        b.y0 = u0; b.rows = u1 - u0;
+        b.rows_above = u0 < p.halo ? u0 : p.halo;
+        b.rows_below = (p.height - u1) < p.halo ? (p.height - u1) : p.halo;
+        b.above = b.rows_above ? c.d_in + (u0 - b.rows_above) * p.pitch : nullptr;
+        b.below = b.rows_below ? c.d_in + u1 * p.pitch : nullptr;
+        e = enqueue(p.kind, c.d_in + u0 * p.pitch, out_base + u0 * p.pitch, p.width, p.height, p.channels, 1, p.sigma,
+                    p.radius, p.level, p.n > 1 ? &b : nullptr, c.s_k);
+    } else {
+        e = enqueue(p.kind, c.d_in + u0 * p.unit_bytes, out_base + u0 * p.unit_bytes, p.width, p.height, p.channels,
+                    u1 - u0, p.sigma, p.radius, p.level, nullptr, c.s_k);
+    }
+    cudaEventRecord(c.k1[k], c.s_k);
+    if (e != cudaSuccess) return e;
+    cudaStreamWaitEvent(c.s_out, c.k1[k], 0);
+    e = cudaMemcpyAsync(p.dst + p.off(k), c.d_out + p.off(k), p.len(k), cudaMemcpyDeviceToHost, c.s_out);
+    cudaEventRecord(c.down[k], c.s_out);
+    return e;
+}
+
+// Pageable caller memory: helper threads copy slices of every chunk into / out of the pinned staging buffers
+// while the calling thread issues the kernels.  Progress is published through per-chunk atomics.
+struct HostProgress {
+    std::atomic<int> staged[kMaxChunks];     // slices of chunk k copied into p_in
+    std::atomic<int> uploaded[kMaxChunks];   // up[k] has been recorded
+    std::atomic<int> issued[kMaxChunks];     // down[k] has been recorded (or the call failed before it)
+    std::atomic<int> err{0};
+    HostProgress() {
+        for (int i = 0; i < kMaxChunks; i++) { staged[i].store(0); uploaded[i].store(0); issued[i].store(0); }
+    }
+    void fail(cudaError_t e) { int zero = 0; if (e != cudaSuccess) err.compare_exchange_strong(zero, (int)e); }
+};
+static void slice_of(size_t len, int j, int parts, size_t* a, size_t* b) {
+    const size_t step = ((len + parts - 1) / parts + 63) & ~(size_t)63;
+    *a = step * j < len ? step * j : len;
+    *b = step * (j + 1) < len ? step * (j + 1) : len;
+}
+static void wait_flag(const std::atomic<int>& f) {
+    for (int spin = 0; f.load(std::memory_order_acquire) == 0; spin++)
+        if (spin > 64) std::this_thread::yield();
+}
+
 // bindings.cpp:37-42, :57-63, :77-81 -- H2D, filter, D2H.  Here: cached device buffers, pinned staging (skipped
-// when the caller's memory is already pinned), and the transfer is cut into chunks (row bands of one image,
-// or image ranges of a batch) so that the upload of chunk k+1, the kernel of chunk k and the download of
-// chunk k-1 overlap: PCIe runs in both directions at once instead of H2D, kernel, D2H back to back.
+// when the caller's memory is already pinned), and the transfer is cut into chunks so that the upload of chunk
+// k+2, the kernel of chunk k and the download of chunk k-1 overlap: PCIe runs in both directions at once
+// instead of H2D, kernel, D2H back to back.
 static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out, int64_t width,
                             int64_t height, int channels, int64_t batch, float sigma, int radius,
                             int level, gip_metrics* metrics) {
@@ -255,73 +346,120 @@ static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out
     if (!h_in || !h_out || width <= 0 || height <= 0 || batch <= 0) return cudaErrorInvalidValue;
     if (channels != 1 && channels != 3 && channels != 4) return cudaErrorInvalidValue;
     if (kind != kSobel && radius < 0) return cudaErrorInvalidValue;
-    const int halo = kind == kSobel ? 1 : radius;
-    const int64_t pitch = width * channels;
-    const size_t bytes = (size_t)pitch * height * batch;
+    HostPlan p;
+    p.kind = kind; p.width = width; p.height = height; p.channels = channels; p.batch = batch;
+    p.sigma = sigma; p.radius = radius; p.level = level;
+    p.halo = kind == kSobel ? 1 : radius;
+    p.pitch = width * channels;
+    const size_t bytes = (size_t)p.pitch * height * batch;
     std::lock_guard<std::mutex> lock(g_cache.mu);
     const bool pin_in = is_pinned(h_in), pin_out = is_pinned(h_out);
-    cudaError_t err = g_cache.ensure(bytes, !(pin_in && pin_out));
+    cudaError_t err = g_cache.ensure(bytes, !pin_in, !pin_out);
     if (err != cudaSuccess) return err;
     HostCache& c = g_cache;
 
-    // chunks: units are rows (one image) or images (a batch); about 8 MB each, at most kMaxChunks
-    const bool by_rows = batch == 1;
-    const int64_t units = by_rows ? height : batch;
-    const int64_t unit_bytes = by_rows ? pitch : pitch * height;
-    int64_t n = (int64_t)(bytes / (8u << 20));
+    // chunks: units are rows (one image) or images (a batch)
+    p.by_rows = batch == 1;
+    p.units = p.by_rows ? height : batch;
+    p.unit_bytes = p.by_rows ? p.pitch : p.pitch * height;
+    int64_t n = (int64_t)(bytes / host_chunk_bytes());
     if (n > kMaxChunks) n = kMaxChunks;
-    if (n > units) n = units;
-    if (by_rows && halo > 0 && n > 1 && units / n < 4 * (int64_t)halo) n = units / (4 * (int64_t)halo);
+    if (n > p.units) n = p.units;
+    if (p.by_rows && p.halo > 0 && n > 1 && p.units / n < 4 * (int64_t)p.halo) n = p.units / (4 * (int64_t)p.halo);
     if (n < 1) n = 1;
-    auto lo_of = [&](int64_t k) { return units * k / n; };
+    p.n = n;
+    p.src = pin_in ? h_in : c.p_in;
+    p.dst = pin_out ? h_out : c.p_out;
 
-    const uint8_t* src = pin_in ? h_in : c.p_in;
-    uint8_t* dst = pin_out ? h_out : c.p_out;
-    auto compute = [&](int64_t k) -> cudaError_t {           // chunk k: kernel + download, after the uploads it needs
-        const int64_t u0 = lo_of(k), u1 = lo_of(k + 1);
-        cudaStreamWaitEvent(c.s_out, c.up[k + 1 < n ? k + 1 : k], 0);   // halo rows below live in chunk k+1
-        cudaEventRecord(c.k0[k], c.s_out);
-        cudaError_t e;
-        if (by_rows) {
-            BandArgs b;
-            b.y0 = u0; b.rows = u1 - u0;
-            b.rows_above = u0 < halo ? u0 : halo;
-            b.rows_below = (height - u1) < halo ? (height - u1) : halo;
-            b.above = b.rows_above ? c.d_in + (u0 - b.rows_above) * pitch : nullptr;
-            b.below = b.rows_below ? c.d_in + u1 * pitch : nullptr;
-            e = enqueue(kind, c.d_in + u0 * pitch, c.d_out + u0 * pitch, width, height, channels, 1, sigma, radius,
-                        level, n > 1 ? &b : nullptr, c.s_out);
-        } else {
-            e = enqueue(kind, c.d_in + u0 * unit_bytes, c.d_out + u0 * unit_bytes, width, height, channels, u1 - u0,
-                        sigma, radius, level, nullptr, c.s_out);
+    const bool threaded = (!pin_in || !pin_out) && bytes >= ((size_t)2 << 20);
+    if (verbose()) cudaEventRecord(c.t0, c.s_in);
+    double host_us[kMaxChunks + 1] = {};
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_now = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count(); };
+    if (!threaded) {
+        for (int64_t k = 0; k < n && err == cudaSuccess; k++) {
+            if (!pin_in) memcpy(c.p_in + p.off(k), h_in + p.off(k), p.len(k));
+            host_us[k] = host_now();
+            err = issue_upload(p, c, k);
+            if (err == cudaSuccess && k >= 1) err = issue_compute(p, c, k - 1);
         }
-        cudaEventRecord(c.k1[k], c.s_out);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(dst + u0 * unit_bytes, c.d_out + u0 * unit_bytes, (size_t)((u1 - u0) * unit_bytes),
-                            cudaMemcpyDeviceToHost, c.s_out);
-        cudaEventRecord(c.down[k], c.s_out);
-        return e;
-    };
-    for (int64_t k = 0; k < n && err == cudaSuccess; k++) {
-        const int64_t u0 = lo_of(k), u1 = lo_of(k + 1);
-        const size_t off = (size_t)(u0 * unit_bytes), len = (size_t)((u1 - u0) * unit_bytes);
-        if (!pin_in) memcpy(c.p_in + off, h_in + off, len);       // overlaps the DMA of the previous chunk
-        err = cudaMemcpyAsync(c.d_in + off, src + off, len, cudaMemcpyHostToDevice, c.s_in);
-        cudaEventRecord(c.up[k], c.s_in);
-        if (err == cudaSuccess && k >= 1) err = compute(k - 1);
+        if (err == cudaSuccess) err = issue_compute(p, c, n - 1);
+        host_us[n] = host_now();
+        if (err != cudaSuccess) {
+            cudaStreamSynchronize(c.s_in); cudaStreamSynchronize(c.s_k); cudaStreamSynchronize(c.s_out);
+            return err;
+        }
+        for (int64_t k = 0; k < n; k++) {                          // drain in order: chunk k while k+1 is in flight
+            if ((err = cudaEventSynchronize(c.down[k])) != cudaSuccess) return err;
+            if (!pin_out) memcpy(h_out + p.off(k), c.p_out + p.off(k), p.len(k));
+        }
+    } else {
+        HostProgress prog;
+        const int dev = c.device;
+        const int t_in = pin_in ? 0 : host_threads() / 2, t_out = pin_out ? 0 : host_threads() - host_threads() / 2;
+        std::vector<std::thread> workers;
+        for (int j = 0; j < t_in; j++)
+            workers.emplace_back([&, j] {                          // stage slice j of every chunk; last one in uploads
+                cudaSetDevice(dev);
+                for (int64_t k = 0; k < n; k++) {
+                    size_t a, b;
+                    slice_of(p.len(k), j, t_in, &a, &b);
+                    if (b > a) memcpy(c.p_in + p.off(k) + a, h_in + p.off(k) + a, b - a);
+                    if (prog.staged[k].fetch_add(1, std::memory_order_acq_rel) == t_in - 1) {
+                        if (k > 0) wait_flag(prog.uploaded[k - 1]);          // keep s_in in chunk order
+                        prog.fail(issue_upload(p, c, k));
+                        prog.uploaded[k].store(1, std::memory_order_release);
+                    }
+                }
+            });
+        for (int j = 0; j < t_out; j++)
+            workers.emplace_back([&, j] {                          // drain slice j of every chunk
+                cudaSetDevice(dev);
+                for (int64_t k = 0; k < n; k++) {
+                    wait_flag(prog.issued[k]);
+                    if (prog.err.load() != 0) continue;
+                    cudaError_t e = cudaEventSynchronize(c.down[k]);
+                    if (e != cudaSuccess) { prog.fail(e); continue; }
+                    size_t a, b;
+                    slice_of(p.len(k), j, t_out, &a, &b);
+                    if (b > a) memcpy(h_out + p.off(k) + a, c.p_out + p.off(k) + a, b - a);
+                }
+            });
+        for (int64_t k = 0; k < n; k++) {
+            if (pin_in) {
+                prog.fail(issue_upload(p, c, k));
+                if (k >= 1 && prog.err.load() == 0) prog.fail(issue_compute(p, c, k - 1));
+                if (k >= 1) prog.issued[k - 1].store(1, std::memory_order_release);
+            } else {
+                wait_flag(prog.uploaded[k + 1 < n ? k + 1 : k]);
+                if (prog.err.load() == 0) prog.fail(issue_compute(p, c, k));
+                prog.issued[k].store(1, std::memory_order_release);
+            }
+        }
+        if (pin_in) {
+            if (prog.err.load() == 0) prog.fail(issue_compute(p, c, n - 1));
+            prog.issued[n - 1].store(1, std::memory_order_release);
+        }
+        for (std::thread& t : workers) t.join();
+        cudaError_t e1 = cudaStreamSynchronize(c.s_in), e2 = cudaStreamSynchronize(c.s_k), e3 = cudaStreamSynchronize(c.s_out);
+        if (prog.err.load() != 0) return (cudaError_t)prog.err.load();
+        if (e1 != cudaSuccess) return e1;
+        if (e2 != cudaSuccess) return e2;
+        if (e3 != cudaSuccess) return e3;
     }
-    if (err == cudaSuccess) err = compute(n - 1);
-    if (err != cudaSuccess) { cudaStreamSynchronize(c.s_in); cudaStreamSynchronize(c.s_out); return err; }
     float ms_total = 0.0f;
-    for (int64_t k = 0; k < n; k++) {                              // drain in order: copy out chunk k while k+1 is still in flight
-        if ((err = cudaEventSynchronize(c.down[k])) != cudaSuccess) return err;
-        if (!pin_out) {
-            const size_t off = (size_t)(lo_of(k) * unit_bytes), len = (size_t)((lo_of(k + 1) - lo_of(k)) * unit_bytes);
-            memcpy(h_out + off, c.p_out + off, len);
-        }
+    for (int64_t k = 0; k < n; k++) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, c.k0[k], c.k1[k]);
         ms_total += ms;
+        if (verbose()) {                                           // device timeline of the pipeline, ms since the call began
+            float a = 0, b = 0, d = 0, e = 0;
+            cudaEventElapsedTime(&a, c.t0, c.up[k]); cudaEventElapsedTime(&b, c.t0, c.k0[k]);
+            cudaEventElapsedTime(&d, c.t0, c.k1[k]); cudaEventElapsedTime(&e, c.t0, c.down[k]);
+            fprintf(stderr, "gip: chunk %2d/%d  host issue %.3f  uploaded %.3f  kernel %.3f..%.3f  downloaded %.3f\n", (int)k, (int)n,
+                    host_us[k] * 1e-3, a, b, d, e);
+            if (k == n - 1) fprintf(stderr, "gip: all issued at host %.3f ms\n", host_us[n] * 1e-3);
+        }
     }
     fill_metrics(metrics, ms_total, kind, (int64_t)bytes);
     return cudaSuccess;

@@ -411,7 +411,7 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     // the largest band count with tiles <= m * resident CTAs for the smallest m that yields a band.
     const int64_t per_band = (int64_t)tl.strips * job.batch;
     const int64_t resident = (int64_t)g_num_sms * ctas_per_sm;
-    int64_t min_rows = 4 * (2 * r + 1); if (min_rows < 32) min_rows = 32;
+    const int64_t min_rows = 16;   // small images: short bands re-filter more halo rows but the march is latency-bound
     int64_t max_bands = rows / min_rows; if (max_bands < 1) max_bands = 1;
     int64_t want = 1;
     for (int m = 1; m <= 64; m++) {

@@ -269,3 +269,43 @@ def test_frame_stream_c4_subset():
             want = {"gaussian": lambda: O.gaussian_blur(f, 2.0, 3), "box": lambda: O.box_blur(f, 3),
                     "sobel": lambda: O.sobel(f, 1)}[kind]()
             _check(kind, fast[i].cpu().numpy(), want, f"c4 frame {i} {kind}")
+
+
+@pytest.mark.parametrize("pin_in,pin_out", [(False, False), (True, False), (False, True), (True, True)])
+def test_host_pipeline_chunked_large_buffers(pin_in, pin_out):
+    """gip_*_host on buffers big enough for the chunked three-stream pipeline (and, for pageable caller memory,
+    the staging threads): one 32 MB image in row chunks with halos, and a batch of frames in image chunks."""
+    import torch
+    L = _lib.load()
+    m = _lib.Metrics()
+
+    def buf(shape, pinned):
+        t = torch.empty(shape, dtype=torch.uint8)
+        return t.pin_memory() if pinned else t
+
+    def run(kind, img, *args):
+        x = buf(img.shape, pin_in)
+        y = buf(img.shape, pin_out)
+        x.numpy()[...] = img
+        y.numpy()[...] = 0xAB
+        if img.ndim == 4:
+            b, h, w, c = img.shape
+        else:
+            (h, w, c), b = img.shape, 1
+        fn = {"box": L.gip_box_blur_host, "gaussian": L.gip_gaussian_blur_host, "sobel": L.gip_sobel_host}[kind]
+        _lib.check(fn(x.data_ptr(), y.data_ptr(), w, h, c, b, *args, ctypes.byref(m)))
+        assert m.time_ms > 0
+        return y.numpy().copy()
+
+    img = synth.uniform(2048, 4096, 4, seed=99)
+    _check("box", run("box", img, 5, 2), O.box_blur(img, 5), "box rows")
+    _check("box", run("box", img, 31, 2), O.box_blur(img, 31), "box rows r31")
+    _check("gaussian", run("gaussian", img, 2.0, 3, 1), O.gaussian_blur(img, 2.0, 3), "gaussian rows")
+    _check("sobel", run("sobel", img, 1), O.sobel(img, 1), "sobel rows")
+    frames = synth.uniform(24 * 540, 960, 3, seed=5).reshape(24, 540, 960, 3)
+    got = run("box", frames, 3, 2)
+    for i in (0, 7, 23):
+        _check("box", got[i], O.box_blur(frames[i], 3), f"frame {i}")
+    got = run("sobel", frames, 2)
+    for i in (0, 11, 23):
+        _check("sobel", got[i], O.sobel(frames[i], 2), f"frame {i}")

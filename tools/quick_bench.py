@@ -56,6 +56,11 @@ if __name__ == "__main__":
         run("box", (4096, 4096, 4), 4, radii)
         run("box", (4320, 7680, 3), 3, radii)
         run("box", (4096, 4096, 1), 8, radii)
+    if what == "small":                     # latency of small single images
+        for shape in ((1080, 1920, 3), (2146, 3239, 3), (256, 4096, 4), (480, 640, 3)):
+            run("box", shape, 16, radii)
+            run("sobel", shape, 16, [1])
+            run("gaussian", shape, 16, [3])
     if what in ("gaussian", "all"):
         run("gaussian", (2146, 3239, 3), 8, [3])
         run("gaussian", (4320, 7680, 3), 3, [3, 15])
