@@ -44,6 +44,10 @@ __device__ __forceinline__ uint64_t to_float_pair(uint32_t lo_byte, uint32_t hi_
     // bytes (already zero-extended) -> floats: OR into the mantissa of 2^23, subtract 2^23
     return add_rn_x2(pack_f2(lo_byte | 0x4B000000u, hi_byte | 0x4B000000u), splat_f2(-8388608.0f));
 }
+// same, for words that already carry the 2^23 exponent (PRMT of a byte over 0x4B000000)
+__device__ __forceinline__ uint64_t byte_pair_to_float(uint32_t lo_biased, uint32_t hi_biased) {
+    return add_rn_x2(pack_f2(lo_biased, hi_biased), splat_f2(-8388608.0f));
+}
 __device__ __forceinline__ uint64_t round_pair(uint64_t acc) {
     return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
 }
@@ -51,7 +55,7 @@ __device__ __forceinline__ uint64_t round_pair(uint64_t acc) {
 // ------------------------------------------------------------------------------------------------
 // H pass.  Image rows [ty0, ty1) of every image of the chunk -> scratch image `tmp` (same pitch).
 // ------------------------------------------------------------------------------------------------
-template <int R, int C, bool kVec>
+template <int R, int C>
 __global__ void __launch_bounds__(HCfg<C, R>::kThreads, 1)
 gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int tiles_x, int tiles_y, int in_pitch, int out_pitch, int64_t tpitch) {
@@ -60,7 +64,7 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     constexpr int TW = HCfg<C, R>::kTilePixels;
     constexpr int kSegPixels = HCfg<C, R>::kSegPixels;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t W = job.width, pitch = job.src.pitch;
+    const int64_t pitch = job.src.pitch;
     unsigned t = blockIdx.x;
     const int tx = (int)(t % (unsigned)tiles_x); t /= (unsigned)tiles_x;
     const int ty = (int)(t % (unsigned)tiles_y);
@@ -70,33 +74,76 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     const int64_t gx0 = (int64_t)tx * TW;                       // first output pixel of the tile
     const int64_t b0 = (gx0 - R) * C;                           // image-row byte position of tile byte 0
     const int tile_bytes = (TW + 2 * R) * C;
-    const int skew = kVec ? (int)(((b0 % 4) + 4) % 4) : 0;      // keeps 4-byte chunks aligned on both sides
     uint8_t* in_tile = smem;
     uint8_t* out_tile = smem + (size_t)kTileRows * in_pitch;
+    constexpr int kWarps = HCfg<C, R>::kThreads / 32;
+    // Tile byte 0 of row rr sits at in_tile + rr*in_pitch + skew(rr), skew(rr) = (global address of that byte) mod 4:
+    // whatever the image pitch and base alignment are, 4-byte chunks are then aligned on both sides of cp.async.
+    auto row_skew = [&](const uint8_t* rowp) { return (int)(((intptr_t)rowp + b0) & 3); };
+    // global pointer of tile row rr: plain pitch arithmetic when the whole tile lies inside the caller's band
+    const bool in_band = row0 >= job.src.band_y0 && row0 + nrows <= job.src.band_y1;
+    const uint8_t* const band_row0 = job.src.band + img * job.src.image_stride + (row0 - job.src.band_y0) * pitch;
+    auto tile_row = [&](int rr) { return in_band ? band_row0 + (int64_t)rr * pitch : job.src.row(row0 + rr, img); };
 
     // ---- stage: bytes [lo, hi) of each row are real image bytes, the rest is clamp-to-edge replication
     const int64_t lo = b0 < 0 ? 0 : b0;
     int64_t hi = b0 + tile_bytes; if (hi > pitch) hi = pitch;
-    if (kVec) {
-        // 4-byte cp.async: the odd-word row pitch that makes the byte loads conflict-free rules out 16-byte chunks
-        const int64_t cs = lo & ~int64_t(3);
-        int64_t ce = (hi + 3) & ~int64_t(3); if (ce > pitch) ce = pitch;
-        const int nchunk = ce > cs ? (int)((ce - cs) >> 2) : 0;
+    {
+        const int n = hi > lo ? (int)(hi - lo) : 0;
         const uint32_t in_s = smem_addr(in_tile);
-        for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
-            const uint8_t* src = job.src.row(row0 + rr, img) + cs;
-            const uint32_t dst = in_s + (uint32_t)(rr * in_pitch + skew + (int)(cs - b0));
-            for (int ci = lane; ci < nchunk; ci += 32) cp_async4(dst + 4 * ci, src + 4 * ci);
+        constexpr int kRowsPerWarp = (kTileRows + kWarps - 1) / kWarps;
+        constexpr int kChunkIters = ((TW + 2 * R) * C / 4 + 31) / 32;     // 4-byte chunks of a tile row per lane
+        // Whole 4-byte chunks go through cp.async.  The up to 3 bytes before the first aligned chunk and after the
+        // last one are plain loads by lanes 0-2 and 4-6: all rows' loads are issued before any is stored, so
+        // their latency is paid once, under the asynchronous copies.
+        uint8_t edge_byte[kRowsPerWarp];
+        int edge_off[kRowsPerWarp];
+        // per row: skew, bytes before the first aligned chunk, whole chunks, this lane's edge byte (or -1)
+        auto row_layout = [&](const uint8_t* rowp, int& skew, int& head, int& nchunk, int& e) {
+            skew = row_skew(rowp);
+            head = (int)((-(intptr_t)(rowp + lo)) & 3); if (head > n) head = n;
+            nchunk = (n - head) >> 2;
+            const int tail0 = head + 4 * nchunk;
+            e = lane < 4 ? (lane < head ? lane : -1) : (lane - 4 < n - tail0 && lane < 8 ? tail0 + lane - 4 : -1);
+        };
+        auto stage_row = [&](int i, int rr, const uint8_t* rowp, int skew, int head, int nchunk, int e) {
+            const uint8_t* g = rowp + lo;
+            const int off = rr * in_pitch + skew + (int)(lo - b0);
+            if (e >= 0) { edge_byte[i] = g[e]; edge_off[i] = off + e; }
+            const uint8_t* gp = g + head + 4 * lane;
+            const uint32_t dp = in_s + (uint32_t)(off + head + 4 * lane);
+            const int mine = nchunk - lane;                        // this lane copies chunks lane, lane+32, ...
+#pragma unroll
+            for (int it = 0; it < kChunkIters; it++)
+                if (mine > 32 * it) cp_async4(dp + 128 * it, gp + 128 * it);
+        };
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; i++) edge_off[i] = -1;
+        if (in_band && (pitch & 3) == 0) {                         // every row of the tile has the same layout
+            int skew, head, nchunk, e;
+            row_layout(band_row0, skew, head, nchunk, e);
+#pragma unroll
+            for (int i = 0; i < kRowsPerWarp; i++) {
+                const int rr = warp + i * kWarps;
+                if (rr < nrows) stage_row(i, rr, band_row0 + (int64_t)rr * pitch, skew, head, nchunk, e);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRowsPerWarp; i++) {
+                const int rr = warp + i * kWarps;
+                if (rr < nrows) {
+                    const uint8_t* rowp = tile_row(rr);
+                    int skew, head, nchunk, e;
+                    row_layout(rowp, skew, head, nchunk, e);
+                    stage_row(i, rr, rowp, skew, head, nchunk, e);
+                }
+            }
         }
         cp_async_commit();
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; i++)
+            if (edge_off[i] >= 0) in_tile[edge_off[i]] = edge_byte[i];
         cp_async_wait<0>();
-    } else {               // rows that are not 4-byte aligned: a warp per row, plain byte copies
-        const int n = hi > lo ? (int)(hi - lo) : 0;
-        for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
-            const uint8_t* src = job.src.row(row0 + rr, img) + lo;
-            uint8_t* dst = in_tile + rr * in_pitch + (int)(lo - b0);
-            for (int i = lane; i < n; i += 32) dst[i] = src[i];
-        }
     }
     __syncthreads();
     {   // replicate the edge pixel into the halo outside the image (left of pixel 0, right of pixel W-1)
@@ -104,8 +151,8 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         const int nr = (b0 + tile_bytes > pitch) ? (int)(b0 + tile_bytes - pitch) : 0;
         const int first_r = tile_bytes - nr;
         if (nl + nr > 0) {
-            for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {
-                uint8_t* rowp = in_tile + rr * in_pitch + skew;
+            for (int rr = warp; rr < nrows; rr += kWarps) {
+                uint8_t* rowp = in_tile + rr * in_pitch + row_skew(tile_row(rr));
                 for (int i = lane; i < nl; i += 32) rowp[i] = rowp[nl + (i % C)];                 // b0 is a multiple of C
                 for (int k = lane; k < nr; k += 32) rowp[first_r + k] = rowp[first_r - C + (k % C)];
             }
@@ -118,8 +165,9 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
         const int ch = warp % C, seg = warp / C;
         const int ra = lane, rb = lane + 32;
         const bool has_a = ra < nrows, has_b = rb < nrows;
-        const uint8_t* pa = in_tile + (has_a ? ra : 0) * in_pitch + skew + seg * kSegPixels * C + ch;
-        const uint8_t* pb = in_tile + (has_b ? rb : 0) * in_pitch + skew + seg * kSegPixels * C + ch;
+        const int rsa = has_a ? ra : 0, rsb = has_b ? rb : 0;
+        const uint8_t* pa = in_tile + rsa * in_pitch + row_skew(tile_row(rsa)) + seg * kSegPixels * C + ch;
+        const uint8_t* pb = in_tile + rsb * in_pitch + row_skew(tile_row(rsb)) + seg * kSegPixels * C + ch;
         uint8_t* qa = out_tile + ra * out_pitch + seg * kSegPixels * C + ch;
         uint8_t* qb = out_tile + rb * out_pitch + seg * kSegPixels * C + ch;
         uint64_t acc[R2];
@@ -155,29 +203,57 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     }
     __syncthreads();
 
-    // ---- copy the output tile to the scratch image (its pitch `tpitch` is a multiple of 16: word stores)
+    // ---- copy the output tile to the scratch image: 16-byte stores (the tile's x origin and the scratch pitch
+    // `tpitch` are multiples of 16; a ragged last group spills into the scratch row's padding)
     const int64_t ob0 = gx0 * C;
     int64_t out_bytes = (int64_t)TW * C; if (ob0 + out_bytes > pitch) out_bytes = pitch - ob0;
     uint8_t* tbase = tmp + ((img - img0) * (ty1 - ty0) + (row0 - ty0)) * tpitch + ob0;
-    const int nv = (int)((out_bytes + 3) >> 2);
-    for (int rr = warp; rr < nrows; rr += HCfg<C, R>::kThreads / 32) {      // a warp per row: coalesced, no index division
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(out_tile + rr * out_pitch);
-        uint32_t* grow = reinterpret_cast<uint32_t*>(tbase + (int64_t)rr * tpitch);
-        for (int ci = lane; ci < nv; ci += 32) grow[ci] = srow[ci];
+    const int nv = (int)((out_bytes + 15) >> 4);
+    const uint32_t out_s = smem_addr(out_tile);
+    for (int rr = warp; rr < nrows; rr += kWarps) {              // a warp per row: coalesced, no index division
+        const uint32_t sp = out_s + (uint32_t)(rr * out_pitch + 16 * lane);
+        uint8_t* gp = tbase + (int64_t)rr * tpitch + 16 * lane;
+        constexpr int kGroupIters = (TW * C / 16 + 31) / 32;
+#pragma unroll
+        for (int it = 0; it < kGroupIters; it++) {
+            if (nv - lane > 32 * it) {
+                uint4 v;
+                v.x = lds32(sp + 512 * it); v.y = lds32(sp + 512 * it + 4); v.z = lds32(sp + 512 * it + 8); v.w = lds32(sp + 512 * it + 12);
+                *reinterpret_cast<uint4*>(gp + 512 * it) = v;
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // V pass.  Scratch rows -> output rows [band_y0, band_y1).  One thread per 4-byte column group.
+// A band is walked in blocks of U = M*R2 input rows (static accumulator slots inside a block):
+//   block 0        the first 2R rows only fill the accumulators (static emit pattern),
+//   steady blocks  every row emits; the next block's rows are prefetched, without clamping when they
+//                  all lie inside the image,
+//   tail           fewer than U rows, guarded.  The host sizes bands to k*U - 2R rows, so that only the
+//                  last band of an image has a tail.
+// kAlignedOut = false: output rows are not 4-byte aligned (odd pitch).  A lane takes the last bytes of its
+// left neighbour's word by shuffle and stores the aligned word that straddles both; the first lane of a
+// warp, the last one and the partial last column store their leftover bytes one by one.
 // ------------------------------------------------------------------------------------------------
+template <int R> struct VCfg {
+    static constexpr int R2 = 2 * R + 1;
+    static constexpr int M = (8 + R2 - 1) / R2;          // blocks per super-block: >= 8 rows of loads in flight
+    static constexpr int U = M * R2;
+};
+
 template <int R, bool kAlignedOut>
 __global__ void __launch_bounds__(128)
 gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int nbands, int band_rows, int words, int64_t tpitch) {
-    constexpr int R2 = 2 * R + 1;
+    constexpr int R2 = VCfg<R>::R2;
+    constexpr int U = VCfg<R>::U;
     const int64_t pitch = job.src.pitch;
-    const int wi = blockIdx.x * 128 + threadIdx.x;
-    if (wi >= words) return;
+    const int wi_raw = blockIdx.x * 128 + threadIdx.x;
+    const bool live = wi_raw < words;
+    if (kAlignedOut && !live) return;                             // (the unaligned variant keeps whole warps for its shuffles)
+    const int wi = live ? wi_raw : words - 1;                     // spare lanes shadow the last column and never store
     const int band = blockIdx.y % nbands;
     const int64_t li = blockIdx.y / nbands;                       // image index inside the chunk
     const int64_t Y0 = job.src.band_y0 + (int64_t)band * band_rows;
@@ -187,18 +263,36 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
     const int nbytes = (pitch - 4 * (int64_t)wi >= 4) ? 4 : (int)(pitch - 4 * (int64_t)wi);
     uint8_t* optr = job.out + (img0 + li) * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + 4 * (int64_t)wi;
     const int64_t H = job.height;
+    // unaligned output only: which stores this thread does for each row misalignment (the same in every lane of a row)
+    const int lane = threadIdx.x & 31;
+    unsigned mis = (unsigned)((uintptr_t)optr & 3);
+    const unsigned mis_step = (unsigned)(pitch & 3);
+    unsigned byte_mask = 0, word_mask = 0;        // nibble m of byte_mask: own bytes stored one by one when mis == m
+    if (!kAlignedOut && live) {
+        const bool full = nbytes == 4;
+        const bool next_full = (wi_raw + 1 < words) && (pitch - 4 * (int64_t)(wi_raw + 1) >= 4);
+        const bool tail_self = lane == 31 || !next_full;      // nobody to the right takes this word's last bytes
+        const unsigned all = (1u << nbytes) - 1;
+        if (full) word_mask |= 1; else byte_mask |= all;
+        for (int m = 1; m < 4; m++) {
+            const unsigned head = (1u << (4 - m)) - 1;        // own bytes that share an aligned word with the left neighbour
+            unsigned nib = 0;
+            if (full && lane > 0) word_mask |= 1u << m; else nib |= head & all;
+            if (tail_self) nib |= all & ~head;
+            byte_mask |= nib << (4 * m);
+        }
+    }
 
     uint64_t acc0[R2], acc1[R2];
 #pragma unroll
     for (int i = 0; i < R2; i++) { acc0[i] = 0; acc1[i] = 0; }
     const int nsteps = (int)(Y1 - Y0) + 2 * R;                    // input rows Y0-R .. Y1-1+R (clamped to the image)
-    constexpr int M = (8 + R2 - 1) / R2;                          // blocks per super-block: >= 8 rows of loads in flight
-    constexpr int U = M * R2;
-    // input row of step s is clamp(Y0 - R + s, 0, H - 1): clamp the step index instead (32-bit), one IMAD.WIDE per load
+    // input row of step s is clamp(Y0 - R + s, 0, H - 1): clamp the step index instead (32-bit)
     const int s_lo = (Y0 - R < 0) ? (int)(R - Y0) : 0;
     const int s_hi_img = (int)(H - 1 - (Y0 - R));
     const int s_hi = s_hi_img < nsteps - 1 ? s_hi_img : nsteps - 1;
     const uint8_t* tbase0 = timg + (Y0 - R - ty0) * tpitch;         // row of step 0 (may lie above the image: never dereferenced unclamped)
+    const unsigned tp32 = (unsigned)tpitch;
     auto load = [&](int s) {
         const int sc = s < s_lo ? s_lo : (s > s_hi ? s_hi : s);
         return __ldg(reinterpret_cast<const uint32_t*>(tbase0 + (int64_t)sc * tpitch));
@@ -206,8 +300,8 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
 #define GIP_V_STEP(WORD, U_, EMIT)                                                                       \
     {                                                                                                    \
         const uint32_t w_ = (WORD);                                                                      \
-        const uint64_t v0 = to_float_pair(w_ & 0xFFu, (w_ >> 8) & 0xFFu);                                \
-        const uint64_t v1 = to_float_pair((w_ >> 16) & 0xFFu, w_ >> 24);                                 \
+        const uint64_t v0 = byte_pair_to_float(__byte_perm(w_, 0x4B000000u, 0x7540), __byte_perm(w_, 0x4B000000u, 0x7541)); \
+        const uint64_t v1 = byte_pair_to_float(__byte_perm(w_, 0x4B000000u, 0x7542), __byte_perm(w_, 0x4B000000u, 0x7543)); \
         acc0[U_] = mul_rn_x2(v0, splat_f2(job.weights[0]));                                              \
         acc1[U_] = mul_rn_x2(v1, splat_f2(job.weights[0]));                                              \
         _Pragma("unroll")                                                                                \
@@ -220,32 +314,59 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
             const uint64_t z0 = round_pair(acc0[((U_) + 1) % R2]), z1 = round_pair(acc1[((U_) + 1) % R2]); \
             const uint32_t t0 = __byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), t1 = __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040); \
             const uint32_t ow_ = __byte_perm(t0, t1, 0x5410);                                            \
-            if (kAlignedOut) stg32_stream(optr, ow_);                                                    \
-            else for (int b_ = 0; b_ < nbytes; b_++) optr[b_] = (uint8_t)(ow_ >> (8 * b_));              \
+            if (kAlignedOut) {                                                                           \
+                stg32_stream(optr, ow_);                                                                 \
+            } else {                                                                                     \
+                const uint32_t left_ = __shfl_up_sync(0xffffffffu, ow_, 1);                              \
+                if ((word_mask >> mis) & 1) stg32_stream(optr - mis, __funnelshift_l(left_, ow_, 8 * mis)); \
+                const unsigned nib_ = (byte_mask >> (4 * mis)) & 15u;                                    \
+                if (nib_) {                                                                              \
+                    if (nib_ & 1) optr[0] = (uint8_t)ow_;                                                \
+                    if (nib_ & 2) optr[1] = (uint8_t)(ow_ >> 8);                                         \
+                    if (nib_ & 4) optr[2] = (uint8_t)(ow_ >> 16);                                        \
+                    if (nib_ & 8) optr[3] = (uint8_t)(ow_ >> 24);                                        \
+                }                                                                                        \
+                mis = (mis + mis_step) & 3;                                                              \
+            }                                                                                            \
             optr += pitch;                                                                               \
         }                                                                                                \
     }
     uint32_t cur[U], nxt[U];
 #pragma unroll
     for (int u = 0; u < U; u++) nxt[u] = load(u);
-    for (int s0 = 0; s0 < nsteps; s0 += U) {
+    int s0 = 0;
+    if (nsteps >= U) {
 #pragma unroll
-        for (int u = 0; u < U; u++) { cur[u] = nxt[u]; nxt[u] = load(s0 + U + u); }
-        if (s0 >= 2 * R && s0 + U <= nsteps) {
+        for (int u = 0; u < U; u++) { cur[u] = nxt[u]; nxt[u] = load(U + u); }
+#pragma unroll
+        for (int u = 0; u < U; u++) GIP_V_STEP(cur[u], u % R2, u >= 2 * R)
+        for (s0 = U; s0 + U <= nsteps; s0 += U) {
+            if (s0 + U >= s_lo && s0 + 2 * U - 1 <= s_hi) {       // the whole prefetched block is inside the image
+                const uint8_t* blk = tbase0 + (int64_t)(s0 + U) * tpitch;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    cur[u] = nxt[u];
+                    nxt[u] = __ldg(reinterpret_cast<const uint32_t*>(blk + (uint64_t)((unsigned)u * tp32)));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; u++) { cur[u] = nxt[u]; nxt[u] = load(s0 + U + u); }
+            }
 #pragma unroll
             for (int u = 0; u < U; u++) GIP_V_STEP(cur[u], u % R2, true)
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++)
-                if (s0 + u < nsteps) GIP_V_STEP(cur[u], u % R2, s0 + u >= 2 * R)
         }
+    }
+    if (s0 < nsteps) {                                            // tail of the band (or a band shorter than one block)
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (s0 + u < nsteps) GIP_V_STEP(nxt[u], u % R2, s0 + u >= 2 * R)
     }
 #undef GIP_V_STEP
 }
 
 template <int R, int C>
 cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, int64_t ty1, int64_t img0, int64_t nimg,
-                     bool vec, cudaStream_t stream) {
+                     cudaStream_t stream) {
     constexpr int TW = HCfg<C, R>::kTilePixels;
     const int tiles_x = (int)((job.width + TW - 1) / TW);
     const int tiles_y = (int)((ty1 - ty0 + kTileRows - 1) / kTileRows);
@@ -256,16 +377,14 @@ cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, 
     const size_t smem = (size_t)kTileRows * (in_pitch + out_pitch);
     const int64_t blocks = (int64_t)tiles_x * tiles_y * nimg;
     if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (vec) {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, true><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
-    } else {
-        static bool set = false;
-        if (!set) { e = cudaFuncSetAttribute(gip_gauss_h<R, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e; set = true; }
-        gip_gauss_h<R, C, false><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y, in_pitch, out_pitch, tpitch);
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(gip_gauss_h<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        set = true;
     }
+    gip_gauss_h<R, C><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y,
+                                                                             in_pitch, out_pitch, tpitch);
     count_launch();
     return cudaGetLastError();
 }
@@ -273,21 +392,32 @@ cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, 
 template <int R>
 cudaError_t launch_v(const Job& job, const uint8_t* tmp, int64_t tpitch, int64_t ty0, int64_t ty1, int64_t img0,
                      int64_t nimg, cudaStream_t stream) {
+    constexpr int U = VCfg<R>::U;
     const int words = (int)((job.src.pitch + 3) / 4);
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     const int64_t col_blocks = (words + 127) / 128;
-    // enough bands to fill the machine (each band re-reads 2R scratch rows)
-    int64_t want = ((int64_t)num_sms() * 16 + col_blocks * nimg - 1) / (col_blocks * nimg);
-    int64_t max_bands = rows / (4 * (2 * R + 1)); if (max_bands < 1) max_bands = 1;
-    if (want > max_bands) want = max_bands;
+    const bool aligned_out = (job.src.pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.out % 4 == 0);
+    static int per_sm[2] = {0, 0};                                // resident blocks per SM of the two variants
+    if (per_sm[aligned_out] == 0) {
+        int n = 0;
+        cudaError_t e = aligned_out ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gip_gauss_v<R, true>, 128, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gip_gauss_v<R, false>, 128, 0);
+        if (e != cudaSuccess) return e;
+        per_sm[aligned_out] = n > 0 ? n : 1;
+    }
+    // Bands: one wave of resident blocks when the image is big enough (each band re-reads 2R scratch rows and
+    // spends its first 2R steps filling accumulators), k*U - 2R rows each so that a band is whole blocks of U steps.
+    const int64_t resident = (int64_t)num_sms() * per_sm[aligned_out];
+    int64_t want = resident / (col_blocks * nimg);
     if (want < 1) want = 1;
-    const int nbands = (int)want;
-    const int band_rows = (int)((rows + nbands - 1) / nbands);
+    int64_t band_rows = (rows + want - 1) / want;
+    band_rows = (band_rows + 2 * R + U - 1) / U * U - 2 * R;
+    if (band_rows < U) band_rows = 2 * U - 2 * R;
+    const int64_t nbands = (rows + band_rows - 1) / band_rows;
     if (nbands * nimg > 65535) return cudaErrorInvalidValue;
     dim3 grid((unsigned)col_blocks, (unsigned)(nbands * nimg));
-    const bool aligned_out = (job.src.pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.out % 4 == 0);
-    if (aligned_out) gip_gauss_v<R, true><<<grid, 128, 0, stream>>>(job, tmp, ty0, ty1, img0, nbands, band_rows, words, tpitch);
-    else             gip_gauss_v<R, false><<<grid, 128, 0, stream>>>(job, tmp, ty0, ty1, img0, nbands, band_rows, words, tpitch);
+    if (aligned_out) gip_gauss_v<R, true><<<grid, 128, 0, stream>>>(job, tmp, ty0, ty1, img0, (int)nbands, (int)band_rows, words, tpitch);
+    else             gip_gauss_v<R, false><<<grid, 128, 0, stream>>>(job, tmp, ty0, ty1, img0, (int)nbands, (int)band_rows, words, tpitch);
     count_launch();
     return cudaGetLastError();
 }
@@ -299,9 +429,6 @@ cudaError_t run_radius(const Job& job, cudaStream_t stream) {
     const int64_t ty0 = clamp64(job.src.band_y0 - R, 0, job.height);
     const int64_t ty1 = clamp64(job.src.band_y1 + R, 0, job.height);
     const int64_t trows = ty1 - ty0;
-    const bool vec = (pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.src.band % 4 == 0) &&
-                     (!job.src.above || (uintptr_t)job.src.above % 4 == 0) &&
-                     (!job.src.below || (uintptr_t)job.src.below % 4 == 0);
     // scratch: whole images of the batch, at most ~1 GiB at a time (and at most 8192 images: grid.y)
     const int64_t tpitch = (pitch + 15) & ~int64_t(15);      // scratch rows are 16-byte aligned whatever the image pitch is
     int64_t chunk = (int64_t(1) << 30) / (trows * tpitch);
@@ -313,9 +440,9 @@ cudaError_t run_radius(const Job& job, cudaStream_t stream) {
     if (err != cudaSuccess) return err;
     for (int64_t img0 = 0; img0 < job.batch && err == cudaSuccess; img0 += chunk) {
         const int64_t n = (job.batch - img0 < chunk) ? job.batch - img0 : chunk;
-        if (C == 4)      err = launch_h<R, 4>(job, tmp, tpitch, ty0, ty1, img0, n, vec, stream);
-        else if (C == 3) err = launch_h<R, 3>(job, tmp, tpitch, ty0, ty1, img0, n, vec, stream);
-        else             err = launch_h<R, 1>(job, tmp, tpitch, ty0, ty1, img0, n, vec, stream);
+        if (C == 4)      err = launch_h<R, 4>(job, tmp, tpitch, ty0, ty1, img0, n, stream);
+        else if (C == 3) err = launch_h<R, 3>(job, tmp, tpitch, ty0, ty1, img0, n, stream);
+        else             err = launch_h<R, 1>(job, tmp, tpitch, ty0, ty1, img0, n, stream);
         if (err == cudaSuccess) err = launch_v<R>(job, tmp, tpitch, ty0, ty1, img0, n, stream);
     }
     cudaError_t ferr = cudaFreeAsync(tmp, stream);
