@@ -108,6 +108,12 @@ __device__ __forceinline__ uint64_t add_rz_x2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t splat_f2(float x) {
     return pack_f2(__float_as_uint(x), __float_as_uint(x));
 }
+// u32 -> f32 (I2FP.F32.U32: 64 lanes/clk/SM on the integer side; the FP32 pipe stays free for the taps)
+__device__ __forceinline__ uint32_t u2f_bits(uint32_t x) {
+    uint32_t r;
+    asm("{.reg .f32 t; cvt.rn.f32.u32 t, %1; mov.b32 %0, t;}" : "=r"(r) : "r"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t lo_f2(uint64_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t hi_f2(uint64_t v) { return (uint32_t)(v >> 32); }
 __device__ __forceinline__ float rsqrt_approx(float x) {

@@ -17,7 +17,7 @@
 //   V pass  (gip_gauss_v)  a thread owns a 4-byte column group and marches down a band of rows straight
 //           from global memory (coalesced 32-bit loads); adjacent bytes are the FFMA2 lanes.
 // Rounding: (uchar)(sum + 0.5f) (:102, :142) == low mantissa byte of RZ((sum + 0.5f) + 2^23).
-// u8 -> float: PRMT into the mantissa of 2^23, minus 2^23 (exact), two values per FADD2.
+// u8 -> float: I2FP.F32.U32 on the zero-extended byte (integer pipe; exact).
 // The algorithm is FP32-issue bound, not HBM bound, from radius 3 up (4r+2 FMAs per byte); DESIGN.md
 // carries the instruction roofline next to the HBM one.
 #pragma once
@@ -41,12 +41,8 @@ template <int C, int R> struct HCfg {
 };
 
 __device__ __forceinline__ uint64_t to_float_pair(uint32_t lo_byte, uint32_t hi_byte) {
-    // bytes (already zero-extended) -> floats: OR into the mantissa of 2^23, subtract 2^23
-    return add_rn_x2(pack_f2(lo_byte | 0x4B000000u, hi_byte | 0x4B000000u), splat_f2(-8388608.0f));
-}
-// same, for words that already carry the 2^23 exponent (PRMT of a byte over 0x4B000000)
-__device__ __forceinline__ uint64_t byte_pair_to_float(uint32_t lo_biased, uint32_t hi_biased) {
-    return add_rn_x2(pack_f2(lo_biased, hi_biased), splat_f2(-8388608.0f));
+    // bytes (already zero-extended) -> floats, exact
+    return pack_f2(u2f_bits(lo_byte), u2f_bits(hi_byte));
 }
 __device__ __forceinline__ uint64_t round_pair(uint64_t acc) {
     return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
@@ -244,7 +240,7 @@ template <int R> struct VCfg {
 };
 
 template <int R, bool kAlignedOut>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (R <= 4) ? 6 : 1)
 gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int nbands, int band_rows, int words, int64_t tpitch) {
     constexpr int R2 = VCfg<R>::R2;
@@ -300,8 +296,8 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
 #define GIP_V_STEP(WORD, U_, EMIT)                                                                       \
     {                                                                                                    \
         const uint32_t w_ = (WORD);                                                                      \
-        const uint64_t v0 = byte_pair_to_float(__byte_perm(w_, 0x4B000000u, 0x7540), __byte_perm(w_, 0x4B000000u, 0x7541)); \
-        const uint64_t v1 = byte_pair_to_float(__byte_perm(w_, 0x4B000000u, 0x7542), __byte_perm(w_, 0x4B000000u, 0x7543)); \
+        const uint64_t v0 = to_float_pair(__byte_perm(w_, 0u, 0x4440), __byte_perm(w_, 0u, 0x4441));      \
+        const uint64_t v1 = to_float_pair(__byte_perm(w_, 0u, 0x4442), __byte_perm(w_, 0u, 0x4443));      \
         acc0[U_] = mul_rn_x2(v0, splat_f2(job.weights[0]));                                              \
         acc1[U_] = mul_rn_x2(v1, splat_f2(job.weights[0]));                                              \
         _Pragma("unroll")                                                                                \

@@ -36,6 +36,9 @@ struct SobelTiling {
 
 struct GrayRow {          // gray of this lane's pixels (0,2), (1,3) and the shifted pairs (-1,1), (2,4)
     uint64_t A, B, PL, PR;
+    // integer gray only (level 2, or gray input): right - left and left + 2*centre + right of this row, for the
+    // pixel pairs (0,2) and (1,3)
+    uint64_t DA, DB, SA, SB;
 };
 
 template <int C>
@@ -92,8 +95,29 @@ __device__ __forceinline__ GrayRow make_gray(const RowWords<C>& r, int lane) {
     const uint32_t right = __shfl_down_sync(0xffffffffu, lo_f2(A), 1);  // pixel 0 of lane+1 == pixel 4
     g.PL = pack_f2(left, lo_f2(B));      // pixels (-1, 1)
     g.PR = pack_f2(hi_f2(A), right);     // pixels ( 2, 4)
+    if (kU8 || C == 1) {
+        const uint64_t kP2 = splat_f2(2.0f);
+        g.DA = sub_rn_x2(B, g.PL);       g.SA = add_rn_x2(fma_rn_x2(A, kP2, g.PL), B);
+        g.DB = sub_rn_x2(g.PR, A);       g.SB = add_rn_x2(fma_rn_x2(B, kP2, A), g.PR);
+    }
     (void)lane;
     return g;
+}
+
+// sqrt(gx^2 + gy^2) of two pixels, rounded like the reference, as float bit patterns whose low byte is the u8.
+__device__ __forceinline__ uint64_t magnitude_pair(uint64_t gx, uint64_t gy) {
+    // fma(gx, gx, gy*gy); the 1e-30 only matters when both gradients are zero (keeps rsqrt finite)
+    const uint64_t m2 = fma_rn_x2(gx, gx, fma_rn_x2(gy, gy, splat_f2(1e-30f)));
+    // sqrtf, the reference's inlined sequence
+    const float r0 = rsqrt_approx(__uint_as_float(lo_f2(m2))), r1 = rsqrt_approx(__uint_as_float(hi_f2(m2)));
+    const uint64_t r = pack_f2(__float_as_uint(r0), __float_as_uint(r1));
+    const uint64_t s0 = mul_rn_x2(m2, r);
+    const uint64_t h = mul_rn_x2(r, splat_f2(0.5f));
+    const uint64_t ns0 = mul_rn_x2(s0, splat_f2(-1.0f));
+    const uint64_t d = fma_rn_x2(ns0, s0, m2);
+    const uint64_t s = fma_rn_x2(d, h, s0);
+    // (uchar)(fminf(s, 255) + 0.5f) == min(trunc(s + 0.5f), 255): the clamp moves to the integer side (see emit)
+    return add_rz_x2(add_rn_x2(s, splat_f2(0.5f)), splat_f2(8388608.0f));
 }
 
 // Sobel magnitude of two pixels, as float bit patterns whose low byte is the rounded u8.
@@ -111,18 +135,17 @@ __device__ __forceinline__ uint64_t sobel_pair(uint64_t TL, uint64_t TC, uint64_
     gy = fma_rn_x2(BC, kP2, gy);
     gx = add_rn_x2(gx, BR);
     gy = add_rn_x2(gy, BR);
-    // fma(gx, gx, gy*gy); the 1e-30 only matters when both gradients are zero (keeps rsqrt finite)
-    const uint64_t m2 = fma_rn_x2(gx, gx, fma_rn_x2(gy, gy, splat_f2(1e-30f)));
-    // sqrtf, the reference's inlined sequence
-    const float r0 = rsqrt_approx(__uint_as_float(lo_f2(m2))), r1 = rsqrt_approx(__uint_as_float(hi_f2(m2)));
-    const uint64_t r = pack_f2(__float_as_uint(r0), __float_as_uint(r1));
-    const uint64_t s0 = mul_rn_x2(m2, r);
-    const uint64_t h = mul_rn_x2(r, splat_f2(0.5f));
-    const uint64_t ns0 = mul_rn_x2(s0, splat_f2(-1.0f));
-    const uint64_t d = fma_rn_x2(ns0, s0, m2);
-    const uint64_t s = fma_rn_x2(d, h, s0);
-    // (uchar)(fminf(s, 255) + 0.5f) == min(trunc(s + 0.5f), 255): the clamp moves to the integer side (see emit)
-    return add_rz_x2(add_rn_x2(s, splat_f2(0.5f)), splat_f2(8388608.0f));
+    return magnitude_pair(gx, gy);
+}
+
+// Integer gray values (level 2 rounds gray to u8, :1443-1444; gray input is u8 already): every partial sum of the
+// reference's gx / gy is an integer below 2^24, so the float32 adds are exact in ANY order and the stencil can be
+// taken apart: gx = D(top) + 2 D(mid) + D(bottom) with D = right - left, gy = S(bottom) - S(top) with
+// S = left + 2 centre + right, D and S computed once per row.  Same bits as the reference, 6 instead of 11 adds.
+__device__ __forceinline__ uint64_t sobel_pair_int(uint64_t Dt, uint64_t Dm, uint64_t Db, uint64_t St, uint64_t Sb) {
+    const uint64_t gx = add_rn_x2(fma_rn_x2(Dm, splat_f2(2.0f), Dt), Db);
+    const uint64_t gy = sub_rn_x2(Sb, St);
+    return magnitude_pair(gx, gy);
 }
 __device__ __forceinline__ uint32_t clamp255(uint32_t z) { return min(z, 0x4B0000FFu); }
 
@@ -182,8 +205,14 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     auto emit = [&](const GrayRow& T, const GrayRow& M, const GrayRow& Bt, int y) {
         uint32_t w[C];
         if (y >= 1 && y <= y_last_interior) {
-            const uint64_t zA = sobel_pair(T.PL, T.A, T.B, M.PL, M.B, Bt.PL, Bt.A, Bt.B);    // pixels 0, 2
-            const uint64_t zB = sobel_pair(T.A, T.B, T.PR, M.A, M.PR, Bt.A, Bt.B, Bt.PR);    // pixels 1, 3
+            uint64_t zA, zB;                                                                  // pixels 0, 2 and 1, 3
+            if (kU8 || C == 1) {
+                zA = sobel_pair_int(T.DA, M.DA, Bt.DA, T.SA, Bt.SA);
+                zB = sobel_pair_int(T.DB, M.DB, Bt.DB, T.SB, Bt.SB);
+            } else {
+                zA = sobel_pair(T.PL, T.A, T.B, M.PL, M.B, Bt.PL, Bt.A, Bt.B);
+                zB = sobel_pair(T.A, T.B, T.PR, M.A, M.PR, Bt.A, Bt.B, Bt.PR);
+            }
             const uint32_t z0 = clamp255(lo_f2(zA)), z2 = clamp255(hi_f2(zA));
             const uint32_t z1 = clamp255(lo_f2(zB)), z3 = clamp255(hi_f2(zB));
             if (C == 1) {

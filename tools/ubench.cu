@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(THREADS) NAME(unsigned* out, long long* cyc, u
 #define B_FFMA_REG(x) asm volatile("{.reg .f32 t,u,v; mov.b32 t, %0; mov.b32 u, %1; mov.b32 v, %2; fma.rn.f32 t, t, u, v; mov.b32 %0, t;}" : "+r"(x) : "r"(b), "r"(c));
 #define B_FADD_RZ(x) asm volatile("{.reg .f32 t; mov.b32 t, %0; add.rz.f32 t, t, 0f4B000000; mov.b32 %0, t;}" : "+r"(x));
 #define B_I2F_U8(x) asm volatile("{.reg .f32 t; cvt.rn.f32.u8 t, %0; mov.b32 %0, t;}" : "+r"(x));
+#define B_I2FP(x)  asm volatile("{.reg .f32 t; cvt.rn.f32.u32 t, %0; mov.b32 %0, t;}" : "+r"(x));
 #define B_F2I(x)   asm volatile("{.reg .f32 t; mov.b32 t, %0; cvt.rzi.u32.f32 %0, t;}" : "+r"(x));
 #define B_RSQ(x)   asm volatile("{.reg .f32 t; mov.b32 t, %0; rsqrt.approx.f32 t, t; mov.b32 %0, t;}" : "+r"(x));
 #define B_SQRT_APPROX(x) asm volatile("{.reg .f32 t; mov.b32 t, %0; sqrt.approx.f32 t, t; mov.b32 %0, t;}" : "+r"(x));
@@ -88,6 +89,7 @@ DEF_U32_KERNEL(k_ffma_imm, B_FFMA)
 DEF_U32_KERNEL(k_ffma_reg, B_FFMA_REG)
 DEF_U32_KERNEL(k_fadd_rz, B_FADD_RZ)
 DEF_U32_KERNEL(k_i2f_u8, B_I2F_U8)
+DEF_U32_KERNEL(k_i2fp, B_I2FP)
 DEF_U32_KERNEL(k_f2i, B_F2I)
 DEF_U32_KERNEL(k_rsq, B_RSQ)
 DEF_U32_KERNEL(k_sqrt_approx, B_SQRT_APPROX)
@@ -262,6 +264,7 @@ int main() {
     run_issue("FFMA reg", k_ffma_reg, 1, nsm, 0);
     run_issue("FADD.RZ imm", k_fadd_rz, 1, nsm, 0);
     run_issue("I2F.U8", k_i2f_u8, 1, nsm, 0);
+    run_issue("I2FP.F32.U32", k_i2fp, 1, nsm, 0);
     run_issue("F2I", k_f2i, 1, nsm, 0);
     run_issue("MUFU.RSQ", k_rsq, 1, nsm, 0);
     run_issue("MUFU.SQRT", k_sqrt_approx, 1, nsm, 0);
