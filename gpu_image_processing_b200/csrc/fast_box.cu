@@ -30,6 +30,7 @@
 // exhaustively).  Sums are kept as float bit patterns (2^23+S), and one FFMA2.RZ with per-radius
 // constants (tools/box_magic.py, verified exhaustively in exact arithmetic) leaves
 // floor((S+r)/k) in the low mantissa byte of two sums at once: no integer divide, no I2F/F2I.
+#include <cstdlib>
 #include "common.cuh"
 #include "device_utils.cuh"
 
@@ -39,11 +40,11 @@ namespace {
 constexpr int kLaneWords = 15;
 constexpr int kLaneBytes = 4 * kLaneWords;      // 60
 constexpr int kWarpRun = 32 * kLaneBytes;       // 1920 bytes of recurrence per staged row
-constexpr int kHWarps = 10;                     // producer warps: one staged row each per step
+// Producer warps (HW, a template parameter) stage and filter one row each per step: K = HW rows per step.
+//   HW = 10  448 threads, two CTAs per SM while the ring fits twice (radius <= 16 for RGBA)
+//   HW = 16  640 threads, for the radii whose ring only fits once per SM: one CTA with 20 warps
+constexpr int kHWarpsSmall = 10, kHWarpsBig = 16;
 constexpr int kVWarps = 4;                      // consumer warps: 128 threads x 16-byte column groups >= 1856 bytes
-constexpr int kWarps = kHWarps + kVWarps;
-constexpr int kThreads = 32 * kWarps;           // 448
-constexpr int K = kHWarps;                      // rows per step
 constexpr int kGroupBytes = 16;                 // V-pass column group: one LDS.128 / STG.128
 constexpr uint32_t kBias = 0x4B000000u;         // float 2^23
 constexpr int kSmemLimit = 225 * 1024;
@@ -75,11 +76,12 @@ __device__ __forceinline__ uint32_t round_pack(uint32_t s0, uint32_t s1, uint32_
     return __byte_perm(t0, t1, 0x5410);
 }
 
-template <int C, bool kVec>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int C, bool kVec, int HW>
+__global__ void __launch_bounds__(32 * (HW + kVWarps), HW == kHWarpsSmall ? 2 : 1)
 gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling tl) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NACC = (C == 3) ? 3 : 4;
+    constexpr int kHWarps = HW, K = HW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp < kHWarps;
     const int r = job.radius;
@@ -366,16 +368,17 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
 }
 
 int g_num_sms = 0;
+const int g_box_hw = [] { const char* e = getenv("GIP_BOX_HW"); return e ? atoi(e) : 0; }();   // tuning knob: force 10/16/20/24 producer warps
 
-template <int C, bool kVec>
+template <int C, bool kVec, int HW>
 cudaError_t launch(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, cudaStream_t stream) {
     static bool attr_set = false;   // per instantiation; the opt-in is idempotent
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gip_box_fused<C, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaError_t e = cudaFuncSetAttribute(gip_box_fused<C, kVec, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    gip_box_fused<C, kVec><<<(unsigned)tiles, kThreads, smem, stream>>>(job, tl);
+    gip_box_fused<C, kVec, HW><<<(unsigned)tiles, 32 * (HW + kVWarps), smem, stream>>>(job, tl);
     count_launch();
     return cudaGetLastError();
 }
@@ -400,11 +403,16 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     tl.ring_pitch = ((32 - tl.nw) * kLaneBytes + 15) & ~15;
     const int64_t pitch = job.src.pitch;
     tl.strips = (int)((pitch + tl.useful - 1) / tl.useful);
-    tl.ring_rows = 2 * r + 1 + 2 * K;
     tl.stage_row = (sh + kWarpRun + 31 + 15) & ~15;
-    const size_t smem = (size_t)K * tl.stage_row + (size_t)tl.ring_rows * tl.ring_pitch;
+    auto smem_for = [&](int hw) { return (size_t)hw * tl.stage_row + (size_t)(2 * r + 1 + 2 * hw) * tl.ring_pitch; };
+    // two CTAs of 14 warps per SM while they fit; otherwise one CTA of 20 warps (or of 14 if even that is too big)
+    int hw = kHWarpsBig;
+    if (g_box_hw == 10 || g_box_hw == 16 || g_box_hw == 20 || g_box_hw == 24) hw = g_box_hw;
+    while (hw > kHWarpsSmall && smem_for(hw) > (size_t)kSmemLimit) hw = hw == 24 ? 20 : hw == 20 ? 16 : 10;
+    const int ctas_per_sm = (hw == kHWarpsSmall && smem_for(hw) <= (size_t)kSmemTwoPerSM) ? 2 : 1;
+    tl.ring_rows = 2 * r + 1 + 2 * hw;
+    const size_t smem = smem_for(hw);
     if (smem > (size_t)kSmemLimit) return cudaSuccess;
-    const int ctas_per_sm = smem <= (size_t)kSmemTwoPerSM ? 2 : 1;
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     if (rows > 0x3fffffff) return cudaSuccess;
     // Row bands: whole waves of resident CTAs.  Each band re-filters 2r halo rows, so prefer few, tall bands:
@@ -429,9 +437,12 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
                      (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
                      (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
     cudaError_t err;
-    if (C == 4)      err = vec ? launch<4, true>(job, tl, smem, tiles, stream) : launch<4, false>(job, tl, smem, tiles, stream);
-    else if (C == 3) err = vec ? launch<3, true>(job, tl, smem, tiles, stream) : launch<3, false>(job, tl, smem, tiles, stream);
-    else             err = vec ? launch<1, true>(job, tl, smem, tiles, stream) : launch<1, false>(job, tl, smem, tiles, stream);
+#define GIP_BOX_LAUNCH(C_, HW_) (vec ? launch<C_, true, HW_>(job, tl, smem, tiles, stream) : launch<C_, false, HW_>(job, tl, smem, tiles, stream))
+    if (hw == 24)      err = C == 4 ? GIP_BOX_LAUNCH(4, 24) : C == 3 ? GIP_BOX_LAUNCH(3, 24) : GIP_BOX_LAUNCH(1, 24);
+    else if (hw == 20) err = C == 4 ? GIP_BOX_LAUNCH(4, 20) : C == 3 ? GIP_BOX_LAUNCH(3, 20) : GIP_BOX_LAUNCH(1, 20);
+    else if (hw == 16) err = C == 4 ? GIP_BOX_LAUNCH(4, 16) : C == 3 ? GIP_BOX_LAUNCH(3, 16) : GIP_BOX_LAUNCH(1, 16);
+    else               err = C == 4 ? GIP_BOX_LAUNCH(4, 10) : C == 3 ? GIP_BOX_LAUNCH(3, 10) : GIP_BOX_LAUNCH(1, 10);
+#undef GIP_BOX_LAUNCH
     *handled = (err == cudaSuccess);
     return err;
 }
