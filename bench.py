@@ -327,7 +327,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (measured_traffic() or {}).get("bytes_per_launch"), "traffic_source": (measured_traffic() or {}).get("source"),
-                         "kernel": "gip_box_fused<4,true>", "peak_source": peak_src,
+                         "kernel": "gip_box_fused<4,true,16>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 2 * img_bytes, "us_per_launch": us_per_launch,
                          "frac_of_8TBs_nominal": achieved / 8000.0},
         }

@@ -41,8 +41,10 @@ constexpr int kLaneWords = 15;
 constexpr int kLaneBytes = 4 * kLaneWords;      // 60
 constexpr int kWarpRun = 32 * kLaneBytes;       // 1920 bytes of recurrence per staged row
 // Producer warps (HW, a template parameter) stage and filter one row each per step: K = HW rows per step.
-//   HW = 10  448 threads, two CTAs per SM while the ring fits twice (radius <= 16 for RGBA)
-//   HW = 16  640 threads, for the radii whose ring only fits once per SM: one CTA with 20 warps
+//   HW = 16  640 threads, one CTA of 20 warps per SM: the default.  Measured on 4096x4096 RGBA against two
+//            CTAs of 14 warps: -5 % at r <= 7, -9 % at r = 16, -27 % at r >= 17 (where only one 14-warp CTA fits);
+//            20 or 24 producer warps, or 8 consumer warps on 8-byte column groups, were all slower.
+//   HW = 10  448 threads, two CTAs per SM while the ring fits twice (radius <= 16 for RGBA): kept for A/B runs
 constexpr int kHWarpsSmall = 10, kHWarpsBig = 16;
 constexpr int kVWarps = 4;                      // consumer warps: 128 threads x 16-byte column groups >= 1856 bytes
 constexpr int kGroupBytes = 16;                 // V-pass column group: one LDS.128 / STG.128
@@ -368,7 +370,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
 }
 
 int g_num_sms = 0;
-const int g_box_hw = [] { const char* e = getenv("GIP_BOX_HW"); return e ? atoi(e) : 0; }();   // tuning knob: force 10/16/20/24 producer warps
+const int g_box_hw = [] { const char* e = getenv("GIP_BOX_HW"); return e ? atoi(e) : 0; }();   // GIP_BOX_HW=10: the two-CTA form, for A/B runs
 
 template <int C, bool kVec, int HW>
 cudaError_t launch(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, cudaStream_t stream) {
@@ -407,8 +409,7 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     auto smem_for = [&](int hw) { return (size_t)hw * tl.stage_row + (size_t)(2 * r + 1 + 2 * hw) * tl.ring_pitch; };
     // two CTAs of 14 warps per SM while they fit; otherwise one CTA of 20 warps (or of 14 if even that is too big)
     int hw = kHWarpsBig;
-    if (g_box_hw == 10 || g_box_hw == 16 || g_box_hw == 20 || g_box_hw == 24) hw = g_box_hw;
-    while (hw > kHWarpsSmall && smem_for(hw) > (size_t)kSmemLimit) hw = hw == 24 ? 20 : hw == 20 ? 16 : 10;
+    if (g_box_hw == kHWarpsSmall || smem_for(hw) > (size_t)kSmemLimit) hw = kHWarpsSmall;
     const int ctas_per_sm = (hw == kHWarpsSmall && smem_for(hw) <= (size_t)kSmemTwoPerSM) ? 2 : 1;
     tl.ring_rows = 2 * r + 1 + 2 * hw;
     const size_t smem = smem_for(hw);
@@ -438,10 +439,8 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
                      (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
     cudaError_t err;
 #define GIP_BOX_LAUNCH(C_, HW_) (vec ? launch<C_, true, HW_>(job, tl, smem, tiles, stream) : launch<C_, false, HW_>(job, tl, smem, tiles, stream))
-    if (hw == 24)      err = C == 4 ? GIP_BOX_LAUNCH(4, 24) : C == 3 ? GIP_BOX_LAUNCH(3, 24) : GIP_BOX_LAUNCH(1, 24);
-    else if (hw == 20) err = C == 4 ? GIP_BOX_LAUNCH(4, 20) : C == 3 ? GIP_BOX_LAUNCH(3, 20) : GIP_BOX_LAUNCH(1, 20);
-    else if (hw == 16) err = C == 4 ? GIP_BOX_LAUNCH(4, 16) : C == 3 ? GIP_BOX_LAUNCH(3, 16) : GIP_BOX_LAUNCH(1, 16);
-    else               err = C == 4 ? GIP_BOX_LAUNCH(4, 10) : C == 3 ? GIP_BOX_LAUNCH(3, 10) : GIP_BOX_LAUNCH(1, 10);
+    if (hw == kHWarpsBig) err = C == 4 ? GIP_BOX_LAUNCH(4, kHWarpsBig) : C == 3 ? GIP_BOX_LAUNCH(3, kHWarpsBig) : GIP_BOX_LAUNCH(1, kHWarpsBig);
+    else                  err = C == 4 ? GIP_BOX_LAUNCH(4, kHWarpsSmall) : C == 3 ? GIP_BOX_LAUNCH(3, kHWarpsSmall) : GIP_BOX_LAUNCH(1, kHWarpsSmall);
 #undef GIP_BOX_LAUNCH
     *handled = (err == cudaSuccess);
     return err;
