@@ -309,3 +309,35 @@ def test_host_pipeline_chunked_large_buffers(pin_in, pin_out):
     got = run("sobel", frames, 2)
     for i in (0, 11, 23):
         _check("sobel", got[i], O.sobel(frames[i], 2), f"frame {i}")
+
+
+@pytest.mark.parametrize("c,w", [(3, 323), (1, 1001), (3, 640), (4, 257), (1, 64)])
+@pytest.mark.parametrize("shift", [0, 1, 2, 3, 5])
+def test_unaligned_buffers_and_canaries(c, w, shift, path):
+    """Input and output at every byte alignment inside larger device buffers: the result still matches the oracle and
+    not one byte outside the output image is written (the odd-pitch paths store aligned words that straddle
+    neighbouring lanes' bytes)."""
+    import torch
+    from gpu_image_processing_b200 import device
+    h = 150
+    img = synth.uniform(h, w, c, seed=w * 7 + c + shift)
+    n = img.size
+    pad = 64
+    src = torch.zeros(n + 2 * pad, dtype=torch.uint8, device="cuda")
+    x = src[pad + shift: pad + shift + n].view(h, w, c)
+    x.copy_(torch.from_numpy(img))
+    for kind, call, want in (
+            ("box", lambda o: device.box_blur(x, 5, 2, out=o), O.box_blur(img, 5)),
+            ("box", lambda o: device.box_blur(x, 20, 1, out=o), O.box_blur(img, 20)),
+            ("gaussian", lambda o: device.gaussian_blur(x, 2.0, 3, 1, out=o), O.gaussian_blur(img, 2.0, 3)),
+            ("gaussian", lambda o: device.gaussian_blur(x, 4.0, 9, 2, out=o), O.gaussian_blur(img, 4.0, 9)),
+            ("sobel", lambda o: device.sobel_edge_detection(x, 1, out=o), O.sobel(img, 1)),
+            ("sobel", lambda o: device.sobel_edge_detection(x, 2, out=o), O.sobel(img, 2))):
+        dst = torch.full((n + 2 * pad,), 0xA5, dtype=torch.uint8, device="cuda")
+        o = dst[pad + (shift * 3) % 7: pad + (shift * 3) % 7 + n].view(h, w, c)
+        call(o)
+        torch.cuda.synchronize()
+        got = dst.cpu().numpy()
+        lo = pad + (shift * 3) % 7
+        assert (got[:lo] == 0xA5).all() and (got[lo + n:] == 0xA5).all(), (kind, "wrote outside the output image")
+        _check(kind, got[lo:lo + n].reshape(h, w, c), want, f"{kind} shift={shift}")
