@@ -28,7 +28,7 @@ namespace gip {
 namespace {
 
 constexpr int kMaxFastRadius = 15;
-constexpr int kTileRows = 64;           // H pass: 32 row pairs (rows l and l+32 are one lane's pair)
+constexpr int kTileRows = 32;           // H pass: lane l owns tile row l; the FFMA2 lanes are two segments of that row
 constexpr int kTileBytesMax = 1024;     // H pass: tile width in bytes (256 RGBA / 256 RGB / 1024 gray pixels)
 
 // A thread marches over a segment of kSegPixels pixels (+ 2R of warm-up).  Short segments for small radii double
@@ -37,7 +37,7 @@ template <int C, int R> struct HCfg {
     static constexpr int kSegPixels = (R <= 4) ? 64 : 128;
     static constexpr int kTilePixels = (C == 1) ? 1024 : 256;
     static constexpr int kSegs = kTilePixels / kSegPixels;
-    static constexpr int kThreads = 32 * C * kSegs;
+    static constexpr int kThreads = 32 * C * kSegs / 2;     // a thread marches two segments at once
 };
 
 __device__ __forceinline__ uint64_t to_float_pair(uint32_t lo_byte, uint32_t hi_byte) {
@@ -156,16 +156,15 @@ gip_gauss_h(const __grid_constant__ Job job, uint8_t* __restrict__ tmp, int64_t 
     }
     __syncthreads();
 
-    // ---- march: this thread = (row pair, channel, segment)
+    // ---- march: this thread = (row, channel, segment pair)
     {
+        constexpr int kHalf = HCfg<C, R>::kSegs / 2;           // segment seg and segment seg + kHalf are the FFMA2 lanes
         const int ch = warp % C, seg = warp / C;
-        const int ra = lane, rb = lane + 32;
-        const bool has_a = ra < nrows, has_b = rb < nrows;
-        const int rsa = has_a ? ra : 0, rsb = has_b ? rb : 0;
-        const uint8_t* pa = in_tile + rsa * in_pitch + row_skew(tile_row(rsa)) + seg * kSegPixels * C + ch;
-        const uint8_t* pb = in_tile + rsb * in_pitch + row_skew(tile_row(rsb)) + seg * kSegPixels * C + ch;
-        uint8_t* qa = out_tile + ra * out_pitch + seg * kSegPixels * C + ch;
-        uint8_t* qb = out_tile + rb * out_pitch + seg * kSegPixels * C + ch;
+        const int rs = lane < nrows ? lane : 0;                // rows past the tile's end recompute row 0 into rows nobody copies out
+        const uint8_t* pa = in_tile + rs * in_pitch + row_skew(tile_row(rs)) + seg * kSegPixels * C + ch;
+        const uint8_t* pb = pa + kHalf * kSegPixels * C;
+        uint8_t* qa = out_tile + lane * out_pitch + seg * kSegPixels * C + ch;
+        uint8_t* qb = qa + kHalf * kSegPixels * C;
         uint64_t acc[R2];
 #pragma unroll
         for (int i = 0; i < R2; i++) acc[i] = 0;

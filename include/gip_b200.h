@@ -92,9 +92,11 @@ int gip_sobel_band(const uint8_t* d_band, const uint8_t* d_above, const uint8_t*
 
 /* ---- host buffers: what bindings.cpp does around each call -------------------------------
  * h_input/h_output are ordinary host memory, width*height*channels*batch bytes.  The call
- * stages through cached pinned buffers and cached device buffers, overlaps H2D / kernel / D2H
- * in chunks of whole images when batch>1, and returns when h_output is complete.
- * metrics->time_ms is kernel-only time like the reference's. */
+ * works through cached device buffers in chunks (row bands of one image, image ranges of a
+ * batch): upload, kernel and download of successive chunks overlap on three streams.  Pinned
+ * caller memory is used directly; pageable memory is staged through cached pinned buffers by
+ * helper threads.  Returns when h_output is complete.
+ * metrics->time_ms is kernel-only time like the reference's (the sum over the chunks). */
 int gip_gaussian_blur_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int64_t height,
                            int channels, int64_t batch, float sigma, int radius, int level,
                            gip_metrics* metrics);

@@ -302,6 +302,9 @@ def test_host_pipeline_chunked_large_buffers(pin_in, pin_out):
     _check("box", run("box", img, 31, 2), O.box_blur(img, 31), "box rows r31")
     _check("gaussian", run("gaussian", img, 2.0, 3, 1), O.gaussian_blur(img, 2.0, 3), "gaussian rows")
     _check("sobel", run("sobel", img, 1), O.sobel(img, 1), "sobel rows")
+    one = synth.uniform(1080, 1920, 3, seed=17)                  # 6 MB: a single chunk, still through the staging threads
+    _check("box", run("box", one, 7, 1), O.box_blur(one, 7), "box single chunk")
+    _check("sobel", run("sobel", one, 2), O.sobel(one, 2), "sobel single chunk")
     frames = synth.uniform(24 * 540, 960, 3, seed=5).reshape(24, 540, 960, 3)
     got = run("box", frames, 3, 2)
     for i in (0, 7, 23):
