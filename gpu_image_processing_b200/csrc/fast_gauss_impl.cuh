@@ -9,10 +9,10 @@
 // accumulators (static register indices by unrolling 2r+1 steps; R = radius is a template parameter):
 //   out[o] accumulates  fma(in[o-r], w[0], 0), fma(in[o-r+1], w[1], .), ... fma(in[o+r], w[2r], .)
 // in exactly the reference's tap order (:86-99), so the float32 sums are bit-identical.
-//   H pass  (gip_gauss_h)  a CTA stages a 64-row x 256-pixel tile (+ r pixels of halo, clamp-to-edge)
-//           in shared memory with cp.async.  A thread owns one channel of a row PAIR and marches
-//           along x: the two rows are the two lanes of FFMA2, so one issue slot does two taps.  Lanes of
-//           a warp are 32 different row pairs (odd shared-memory pitch: conflict-free byte loads).
+//   H pass  (gip_gauss_h)  a CTA stages a 32-row x 256-pixel tile (+ r pixels of halo, clamp-to-edge)
+//           in shared memory with cp.async.  A thread owns one channel of one row and marches along
+//           x over TWO segments at once: they are the two lanes of FFMA2, so one issue slot does two
+//           taps.  Lanes of a warp are the 32 rows (odd shared-memory pitch: conflict-free byte loads).
 //           Rounded bytes go to an output tile in shared memory and leave with coalesced 32-bit stores.
 //   V pass  (gip_gauss_v)  a thread owns a 4-byte column group and marches down a band of rows straight
 //           from global memory (coalesced 32-bit loads); adjacent bytes are the FFMA2 lanes.
