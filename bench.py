@@ -241,6 +241,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    placement = {"bound": False, "why": "GIP_BENCH_NO_BIND"}
+    if os.environ.get("GIP_BENCH_NO_BIND") != "1":
+        from gpu_image_processing_b200 import affinity
+        placement = affinity.bind_to_device_numa(local)     # pinned buffers below land on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.load()
@@ -322,7 +327,8 @@ def main():
             "dtype": "u8", "data": "synthetic", "config": CONFIG,
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": img_bytes * len(RADII),
                     "d2h_bytes_per_step": img_bytes * len(RADII), "steps": e2e_steps,
-                    "api": "gip_box_blur_host (C ABI behind gpu_filters.box_blur), pinned host buffers, per-call H2D + kernel + D2H"},
+                    "api": "gip_box_blur_host (C ABI behind gpu_filters.box_blur), pinned host buffers, per-call H2D + kernel + D2H",
+                    "cpu_placement_rank0": placement},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -332,6 +338,7 @@ def main():
                          "frac_of_8TBs_nominal": achieved / 8000.0},
         }
         if world == 1 and not args.no_extras:
+            os.sched_setaffinity(0, all_cpus)                # the CPU baseline gets every core the box gives us
             line["cpu_baseline"], _ = cpu_port_run(1, 1)
             line["reference_cuda_same_gpu"] = reference_cuda_same_gpu(torch, xs[0], ys[0])
             line["filters"] = other_configs(torch, device)
