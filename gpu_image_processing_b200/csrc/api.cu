@@ -118,19 +118,47 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
 
     float* d_wide = nullptr;
     cudaError_t err = cudaSuccess;
+    // In-place calls (d_output overlapping d_input).  The reference's blurs tolerate them because their two passes
+    // go through a temp image (image_filters.cu:760-880); the fused kernels here read halo rows that another CTA
+    // may already have overwritten, so an overlapping input is first copied to stream-ordered scratch.
+    uint8_t* d_copy = nullptr;
+    {
+        const size_t out_bytes = (size_t)job.src.pitch * (size_t)(job.src.band_y1 - job.src.band_y0) * (size_t)batch;
+        const uintptr_t i0 = (uintptr_t)d_in, o0 = (uintptr_t)d_out;
+        if (i0 < o0 + out_bytes && o0 < i0 + out_bytes) {
+            if ((err = cudaMallocAsync((void**)&d_copy, out_bytes, stream)) != cudaSuccess) return err;
+            if ((err = cudaMemcpyAsync(d_copy, d_in, out_bytes, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) {
+                cudaFreeAsync(d_copy, stream);
+                return err;
+            }
+            job.src.band = d_copy;
+        }
+        if (band) {     // halo rows that overlap the output cannot be saved the same way: refuse
+            const size_t ha = (size_t)job.src.pitch * (size_t)band->rows_above, hb = (size_t)job.src.pitch * (size_t)band->rows_below;
+            const uintptr_t a0 = (uintptr_t)band->above, b0 = (uintptr_t)band->below;
+            if ((band->above && a0 < o0 + out_bytes && o0 < a0 + ha) || (band->below && b0 < o0 + out_bytes && o0 < b0 + hb)) {
+                if (d_copy) cudaFreeAsync(d_copy, stream);
+                return cudaErrorInvalidValue;
+            }
+        }
+    }
     if (kind == kGaussian) {
         if (radius <= kMaxFusedRadius) {
             gaussian_weights_host(job.weights, radius, sigma);
         } else {
             const size_t n = 2 * (size_t)radius + 1;
             float* h = (float*)malloc(n * sizeof(float));
-            if (!h) return cudaErrorMemoryAllocation;
+            if (!h) { if (d_copy) cudaFreeAsync(d_copy, stream); return cudaErrorMemoryAllocation; }
             gaussian_weights_host(h, radius, sigma);
             err = cudaMallocAsync((void**)&d_wide, n * sizeof(float), stream);
             if (err == cudaSuccess)   // pageable source: staged before the call returns
                 err = cudaMemcpyAsync(d_wide, h, n * sizeof(float), cudaMemcpyHostToDevice, stream);
             free(h);
-            if (err != cudaSuccess) { if (d_wide) cudaFreeAsync(d_wide, stream); return err; }
+            if (err != cudaSuccess) {
+                if (d_wide) cudaFreeAsync(d_wide, stream);
+                if (d_copy) cudaFreeAsync(d_copy, stream);
+                return err;
+            }
         }
     }
 
@@ -138,6 +166,7 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
     if (g_path.load() == 0 && radius <= kMaxFusedRadius) err = launch_fast(kind, job, stream, &handled);
     if (!handled && err == cudaSuccess) err = launch_general(kind, job, d_wide, stream);
     if (d_wide) cudaFreeAsync(d_wide, stream);
+    if (d_copy) cudaFreeAsync(d_copy, stream);
     return err;
 }
 

@@ -13,7 +13,7 @@
 //           in shared memory with cp.async.  A thread owns one channel of one row and marches along
 //           x over TWO segments at once: they are the two lanes of FFMA2, so one issue slot does two
 //           taps.  Lanes of a warp are the 32 rows (odd shared-memory pitch: conflict-free byte loads).
-//           Rounded bytes go to an output tile in shared memory and leave with coalesced 32-bit stores.
+//           Rounded bytes go to an output tile in shared memory and leave with coalesced 16-byte stores.
 //   V pass  (gip_gauss_v)  a thread owns a 4-byte column group and marches down a band of rows straight
 //           from global memory (coalesced 32-bit loads); adjacent bytes are the FFMA2 lanes.
 // Rounding: (uchar)(sum + 0.5f) (:102, :142) == low mantissa byte of RZ((sum + 0.5f) + 2^23).

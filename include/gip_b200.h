@@ -19,6 +19,10 @@
  *   gip_gaussian_weights
  *       generateGaussianKernel, cuda_lib/src/image_filters.cu:25-39 (without its printf).
  *
+ * In-place calls: d_output may overlap d_input (the reference's blurs tolerate that because they go through a
+ * temp image, image_filters.cu:760-880); the input is then copied to stream-ordered scratch first.  Band calls
+ * return cudaErrorInvalidValue when d_above / d_below overlap d_output.
+ *
  * Image layout everywhere: u8, row-major, interleaved channels,
  *   byte(y, x, c) = base[(y*width + x)*channels + c]           (image_filters.cu:95)
  * channels in {1,3,4}.  A batch is `batch` such images back to back.

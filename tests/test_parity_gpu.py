@@ -344,3 +344,27 @@ def test_unaligned_buffers_and_canaries(c, w, shift, path):
         lo = pad + (shift * 3) % 7
         assert (got[:lo] == 0xA5).all() and (got[lo + n:] == 0xA5).all(), (kind, "wrote outside the output image")
         _check(kind, got[lo:lo + n].reshape(h, w, c), want, f"{kind} shift={shift}")
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_in_place_calls(c, path):
+    """d_output == d_input (and partially overlapping buffers): the reference's blurs tolerate it because they go
+    through a temp image (image_filters.cu:760-880); here an overlapping input is saved to scratch first."""
+    import torch
+    from gpu_image_processing_b200 import device
+    h, w = 300, 412
+    img = synth.uniform(h, w, c, seed=c * 11)
+    n = img.size
+    for kind, call, want in (
+            ("box", lambda x, o: device.box_blur(x, 9, 2, out=o), O.box_blur(img, 9)),
+            ("gaussian", lambda x, o: device.gaussian_blur(x, 2.0, 3, 1, out=o), O.gaussian_blur(img, 2.0, 3)),
+            ("sobel", lambda x, o: device.sobel_edge_detection(x, 1, out=o), O.sobel(img, 1))):
+        x = torch.from_numpy(img).cuda()
+        call(x, x)                                                   # exactly in place
+        _check(kind, x.cpu().numpy(), want, kind + " in place")
+        buf = torch.zeros(n + 4096, dtype=torch.uint8, device="cuda")   # output shifted 1024 bytes into the input
+        xin = buf[:n].view(h, w, c)
+        xin.copy_(torch.from_numpy(img))
+        xout = buf[1024:1024 + n].view(h, w, c)
+        call(xin, xout)
+        _check(kind, xout.cpu().numpy(), want, kind + " overlapping")
