@@ -184,7 +184,8 @@ def reference_cuda_same_gpu(torch, x, y):
 
 
 def other_configs(torch, device_mod):
-    """Device-resident timings of BASELINE configs c1 (Gaussian) and c3 (Sobel): reported, not the headline."""
+    """Device-resident timings of the other BASELINE configs (c1, c3, one GPU's share of c4 and c5): reported, not
+    the headline."""
     out = {}
     g = torch.Generator(device="cuda").manual_seed(7)
 
@@ -204,19 +205,27 @@ def other_configs(torch, device_mod):
     for name, (h, w, c), nb, call in (
             ("c1_gaussian_3239x2146_rgb_s2_r3", (2146, 3239, 3), 8, lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 2, out=y)),
             ("c3_sobel_7680x4320_rgb", (4320, 7680, 3), 3, lambda x, y: device_mod.sobel_edge_detection(x, 1, out=y)),
-            ("box_r3_1920x1080_rgb_x64", (64 * 1080, 1920, 3), 2, None)):
+            ("c3_shape_gaussian_s2_r3", (4320, 7680, 3), 3, lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 1, out=y)),
+            # one GPU's share of c5 at 8 GPUs: a 4096-row band of the 32768-wide image (halo rows included in the input)
+            ("c5_band_gaussian_32768x4096_rgb_s5_r15", (4096, 32768, 3), 2, lambda x, y: device_mod.gaussian_blur(x, 5.0, 15, 1, out=y))):
         try:
-            if call is None:
-                xs = [torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
-                ys = [torch.empty_like(t) for t in xs]
-                out[name] = timed(lambda i: device_mod.box_blur(xs[i % nb], 3, 2, out=ys[i % nb]), xs[0].numel(), 64 * 1080 * 1920)
-            else:
-                xs = [torch.randint(0, 256, (h, w, c), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
-                ys = [torch.empty_like(t) for t in xs]
-                out[name] = timed(lambda i: call(xs[i % nb], ys[i % nb]), h * w * c, h * w)
+            xs = [torch.randint(0, 256, (h, w, c), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
+            ys = [torch.empty_like(t) for t in xs]
+            out[name] = timed(lambda i: call(xs[i % nb], ys[i % nb]), h * w * c, h * w)
             del xs, ys
         except Exception as e:
             out[name] = {"error": repr(e)}
+    try:    # c4: 64 of the 4096 1080p RGB frames, one batched launch per filter
+        nb = 2
+        xs = [torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nb)]
+        ys = [torch.empty_like(t) for t in xs]
+        for name, call in (("c4_box_r3_1920x1080_rgb_x64", lambda x, y: device_mod.box_blur(x, 3, 2, out=y)),
+                           ("c4_sobel_1920x1080_rgb_x64", lambda x, y: device_mod.sobel_edge_detection(x, 1, out=y)),
+                           ("c4_gaussian_s2_r3_1920x1080_rgb_x64", lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 1, out=y))):
+            out[name] = timed(lambda i: call(xs[i % nb], ys[i % nb]), xs[0].numel(), 64 * 1080 * 1920)
+        del xs, ys
+    except Exception as e:
+        out["c4"] = {"error": repr(e)}
     return out
 
 
@@ -342,6 +351,9 @@ def main():
             line["cpu_baseline"], _ = cpu_port_run(1, 1)
             line["reference_cuda_same_gpu"] = reference_cuda_same_gpu(torch, xs[0], ys[0])
             line["filters"] = other_configs(torch, device)
+            for v in line["filters"].values():
+                if "alg_GB/s" in v:
+                    v["frac_of_hbm_peak"] = v["alg_GB/s"] / peak
         emit(line)
     if world > 1:
         dist.barrier()
