@@ -610,6 +610,13 @@ int64_t gip_launch_count(void) { return g_launches.load(); }
 int gip_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_cache.mu);
     g_cache.release();
+    int dev = 0;                                   // also hand the stream-ordered scratch pool back to the driver
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
     return 0;
 }
 const char* gip_version(void) { return "gip_b200 0.1 sm_100a"; }

@@ -127,7 +127,7 @@ int gip_gaussian_weights(float* weights_out, int radius, float sigma);
 const char* gip_error_string(int err);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 int64_t gip_launch_count(void);
-/* Release cached pinned/device staging buffers of the host entry points. */
+/* Release cached pinned/device staging buffers of the host entry points and trim the stream-ordered scratch pool. */
 int gip_release_cache(void);
 /* "gip_b200 <version> sm_100a" */
 const char* gip_version(void);
