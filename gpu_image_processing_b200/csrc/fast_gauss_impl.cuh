@@ -400,14 +400,23 @@ cudaError_t launch_v(const Job& job, const uint8_t* tmp, int64_t tpitch, int64_t
         if (e != cudaSuccess) return e;
         per_sm[aligned_out] = n > 0 ? n : 1;
     }
-    // Bands: one wave of resident blocks when the image is big enough (each band re-reads 2R scratch rows and
-    // spends its first 2R steps filling accumulators), k*U - 2R rows each so that a band is whole blocks of U steps.
+    // Bands.  A block's time is proportional to its steps (band rows + 2R rows that only fill the accumulators), the
+    // launch's to the number of waves of resident blocks: take the band count with the smallest waves x steps.
+    // Bands are k*U - 2R rows so that every band but an image's last is whole blocks of U steps.
     const int64_t resident = (int64_t)num_sms() * per_sm[aligned_out];
-    int64_t want = resident / (col_blocks * nimg);
-    if (want < 1) want = 1;
-    int64_t band_rows = (rows + want - 1) / want;
-    band_rows = (band_rows + 2 * R + U - 1) / U * U - 2 * R;
-    if (band_rows < U) band_rows = 2 * U - 2 * R;
+    int64_t band_rows = rows, best_cost = -1;
+    for (int64_t nb = 1; nb <= 512 && nb <= rows; nb++) {
+        int64_t br = (rows + nb - 1) / nb;
+        br = (br + 2 * R + U - 1) / U * U - 2 * R;
+        while (br < 1) br += U;
+        if (br > rows) br = rows;
+        const int64_t n_actual = (rows + br - 1) / br;
+        if (n_actual * nimg > 65535) continue;
+        const int64_t blocks = col_blocks * n_actual * nimg;
+        const int64_t waves = (blocks + resident - 1) / resident;
+        const int64_t cost = waves * (br + 2 * R + 16);          // + a block's fixed start-up, in row steps
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; band_rows = br; }
+    }
     const int64_t nbands = (rows + band_rows - 1) / band_rows;
     if (nbands * nimg > 65535) return cudaErrorInvalidValue;
     dim3 grid((unsigned)col_blocks, (unsigned)(nbands * nimg));
