@@ -416,19 +416,21 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     if (smem > (size_t)kSmemLimit) return cudaSuccess;
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     if (rows > 0x3fffffff) return cudaSuccess;
-    // Row bands: whole waves of resident CTAs.  Each band re-filters 2r halo rows, so prefer few, tall bands:
-    // the largest band count with tiles <= m * resident CTAs for the smallest m that yields a band.
+    // Row bands.  A tile's time is proportional to its row steps (band rows + 2r halo rows + the pipeline fill), the
+    // launch's to the number of waves of resident CTAs: take the band count with the smallest waves x steps.
     const int64_t per_band = (int64_t)tl.strips * job.batch;
     const int64_t resident = (int64_t)g_num_sms * ctas_per_sm;
     const int64_t min_rows = 16;   // small images: short bands re-filter more halo rows but the march is latency-bound
     int64_t max_bands = rows / min_rows; if (max_bands < 1) max_bands = 1;
-    int64_t want = 1;
-    for (int m = 1; m <= 64; m++) {
-        want = (int64_t)m * resident / per_band;
-        if (want >= 1) break;
+    if (max_bands > 1024) max_bands = 1024;
+    int64_t want = 1, best_cost = -1;
+    for (int64_t nb = 1; nb <= max_bands; nb++) {
+        if (per_band * nb > 0x7fffffff) break;
+        const int64_t waves = (per_band * nb + resident - 1) / resident;
+        const int64_t steps = (rows + nb - 1) / nb + 2 * r + 2 * hw;
+        const int64_t cost = waves * steps;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; want = nb; }
     }
-    if (want < 1) want = 1;
-    if (want > max_bands) want = max_bands;
     tl.bands = (int)want;
     tl.band_rows = (int)((rows + tl.bands - 1) / tl.bands);
     const int64_t tiles = per_band * tl.bands;
