@@ -306,15 +306,20 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     if (rows > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
     const int64_t per_band = (int64_t)tl.strips * job.batch;
+    // Row bands: the band count with the smallest (waves of resident warps) x (rows a warp marches, its 2 halo rows and
+    // the 3-row load pipeline included).  24 warps are resident per SM (3 blocks of 8).  One full wave of tall bands
+    // for a single image (measured on 8K RGB, warps per SM: 24 -> 76.6 us, 25 -> 95.6, 48 -> 78.3, 64 -> 79.9);
+    // several finer waves for batches.
     static const int warps_per_sm = [] { const char* e = getenv("GIP_SOBEL_WARPS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 24; }();
-    // one wave: 24 warps are resident per SM (3 blocks of 8), every warp marches one tall band
-    // (measured on 8K RGB: 24 -> 76.6 us, 48 -> 78.3, 64 -> 79.9, 144 -> 81.8)
-    const int64_t want_tiles = (int64_t)g_num_sms * warps_per_sm;
-    int64_t bands = want_tiles / per_band;                           // whole wave or less
-    if (bands < 1) bands = ((int64_t)g_num_sms * 64 + per_band - 1) / per_band;   // batches: several waves, fine-grained
+    const int64_t resident = (int64_t)g_num_sms * warps_per_sm;
     int64_t max_bands = rows / 24; if (max_bands < 1) max_bands = 1;  // a band re-reads 2 halo rows
-    if (bands > max_bands) bands = max_bands;
-    if (bands < 1) bands = 1;
+    if (max_bands > 1024) max_bands = 1024;
+    int64_t bands = 1, best_cost = -1;
+    for (int64_t nb = 1; nb <= max_bands; nb++) {
+        const int64_t waves = (per_band * nb + resident - 1) / resident;
+        const int64_t cost = waves * ((rows + nb - 1) / nb + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; bands = nb; }
+    }
     tl.bands = (int)bands;
     tl.band_rows = (int)((rows + bands - 1) / bands);
     tl.tiles = per_band * bands;
