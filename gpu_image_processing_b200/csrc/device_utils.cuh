@@ -35,9 +35,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 // streaming global stores / loads (the images are touched once: keep them out of L1)
 __device__ __forceinline__ void stg32_stream(void* p, uint32_t v) {
@@ -53,18 +50,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-// d = c + sum_i a.u8[i] * b.u8[i]   (IDP.4A.U8.U8)
-__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
-__device__ __forceinline__ float fma_rz(float a, float b, float c) {
-    float d;
-    asm("fma.rz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
 
 // packed float pairs (FFMA2 / FADD2): two lanes per issue slot
 __device__ __forceinline__ uint64_t pack_f2(uint32_t lo, uint32_t hi) {
@@ -121,20 +107,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ uint32_t ldg32_nc(const void* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void stg64_stream(void* p, uint2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
-}
 
 // bytes [k, k+4) of the 8-byte little-endian pair (lo, hi), k = shift_bits/8 in 0..3
 __device__ __forceinline__ uint32_t funnel_bytes(uint32_t lo, uint32_t hi, uint32_t shift_bits) {

@@ -7,9 +7,10 @@
 // Decomposition.  A row of the image is a byte stream (pixel x, channel c at byte x*C+c); a
 // horizontal box tap at pixel offset i is byte offset C*i, so the H pass is the same code for
 // C = 1, 3, 4.  A CTA owns a column strip of `useful` output bytes and a band of rows and
-// marches down the band K = 10 rows at a time.  The CTA is warp-specialised: 10 producer warps
+// marches down the band K = 16 rows at a time.  The CTA is warp-specialised: 16 producer warps
 // (stage + H pass, one row each) run one step ahead of 4 consumer warps (V pass + store); one
-// __syncthreads per step hands a step's rows over.  64 registers per thread: two CTAs per SM.
+// __syncthreads per step hands a step's rows over.  640 threads, one CTA per SM (the first shape,
+// 10 + 4 warps and two CTAs per SM, is still instantiated for A/B runs: GIP_BOX_HW=10).
 //   stage   producer warp w copies input row w of the step (strip + halo) into its private
 //           shared-memory row with 16-byte cp.async (LDGSTS), issued as soon as the previous row
 //           has been read into registers, so the copy flies under the arithmetic.
