@@ -239,16 +239,21 @@ template <int R> struct VCfg {
 };
 
 template <int R, bool kAlignedOut>
-__global__ void __launch_bounds__(128, (R <= 4) ? 6 : 1)
+__global__ void __launch_bounds__(128, (R <= 4 && kAlignedOut) ? 6 : 1)
 gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int nbands, int band_rows, int words, int64_t tpitch) {
     constexpr int R2 = VCfg<R>::R2;
     constexpr int U = VCfg<R>::U;
     const int64_t pitch = job.src.pitch;
-    const int wi_raw = blockIdx.x * 128 + threadIdx.x;
-    const bool live = wi_raw < words;
+    const int lane = threadIdx.x & 31;
+    // Column of this thread.  Aligned output: 128 consecutive columns per block.  Unaligned output: consecutive warps
+    // overlap by one column (lane 0 recomputes the previous warp's last column and never stores), so that every
+    // storing lane finds its left neighbour's word in its own warp; a warp then covers 31 columns.
+    const int wi_raw = kAlignedOut ? blockIdx.x * 128 + threadIdx.x
+                                   : (blockIdx.x * 4 + (threadIdx.x >> 5)) * 31 + lane - 1;
+    const bool live = wi_raw >= 0 && wi_raw < words;
     if (kAlignedOut && !live) return;                             // (the unaligned variant keeps whole warps for its shuffles)
-    const int wi = live ? wi_raw : words - 1;                     // spare lanes shadow the last column and never store
+    const int wi = wi_raw < 0 ? 0 : (wi_raw < words ? wi_raw : words - 1);   // spare lanes shadow an edge column and never store
     const int band = blockIdx.y % nbands;
     const int64_t li = blockIdx.y / nbands;                       // image index inside the chunk
     const int64_t Y0 = job.src.band_y0 + (int64_t)band * band_rows;
@@ -258,25 +263,28 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
     const int nbytes = (pitch - 4 * (int64_t)wi >= 4) ? 4 : (int)(pitch - 4 * (int64_t)wi);
     uint8_t* optr = job.out + (img0 + li) * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + 4 * (int64_t)wi;
     const int64_t H = job.height;
-    // unaligned output only: which stores this thread does for each row misalignment (the same in every lane of a row)
-    const int lane = threadIdx.x & 31;
+    // Unaligned output only: which stores this thread does for each row misalignment `mis` (the same in every lane of
+    // a row).  A full column with a left neighbour stores the aligned word [its address - mis, +4) = the neighbour's
+    // last `mis` bytes + its own first 4 - mis.  Bytes nobody's word covers are stored one by one: the first bytes of
+    // column 0, the last bytes of the last full column, the partial last column; those lanes sit in at most two
+    // warps of a row, every other warp skips the byte path as a whole.
     unsigned mis = (unsigned)((uintptr_t)optr & 3);
     const unsigned mis_step = (unsigned)(pitch & 3);
     unsigned byte_mask = 0, word_mask = 0;        // nibble m of byte_mask: own bytes stored one by one when mis == m
-    if (!kAlignedOut && live) {
+    if (!kAlignedOut && live && lane > 0) {
         const bool full = nbytes == 4;
         const bool next_full = (wi_raw + 1 < words) && (pitch - 4 * (int64_t)(wi_raw + 1) >= 4);
-        const bool tail_self = lane == 31 || !next_full;      // nobody to the right takes this word's last bytes
         const unsigned all = (1u << nbytes) - 1;
         if (full) word_mask |= 1; else byte_mask |= all;
         for (int m = 1; m < 4; m++) {
             const unsigned head = (1u << (4 - m)) - 1;        // own bytes that share an aligned word with the left neighbour
             unsigned nib = 0;
-            if (full && lane > 0) word_mask |= 1u << m; else nib |= head & all;
-            if (tail_self) nib |= all & ~head;
+            if (full && wi_raw > 0) word_mask |= 1u << m; else nib |= head & all;
+            if (!next_full) nib |= all & ~head;              // nobody to the right takes this word's last bytes
             byte_mask |= nib << (4 * m);
         }
     }
+    const bool edge_warp = !kAlignedOut && __any_sync(0xffffffffu, byte_mask != 0);
 
     uint64_t acc0[R2], acc1[R2];
 #pragma unroll
@@ -314,8 +322,8 @@ gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, in
             } else {                                                                                     \
                 const uint32_t left_ = __shfl_up_sync(0xffffffffu, ow_, 1);                              \
                 if ((word_mask >> mis) & 1) stg32_stream(optr - mis, __funnelshift_l(left_, ow_, 8 * mis)); \
-                const unsigned nib_ = (byte_mask >> (4 * mis)) & 15u;                                    \
-                if (nib_) {                                                                              \
+                if (edge_warp) {                                                                         \
+                    const unsigned nib_ = (byte_mask >> (4 * mis)) & 15u;                                \
                     if (nib_ & 1) optr[0] = (uint8_t)ow_;                                                \
                     if (nib_ & 2) optr[1] = (uint8_t)(ow_ >> 8);                                         \
                     if (nib_ & 4) optr[2] = (uint8_t)(ow_ >> 16);                                        \
@@ -390,8 +398,8 @@ cudaError_t launch_v(const Job& job, const uint8_t* tmp, int64_t tpitch, int64_t
     constexpr int U = VCfg<R>::U;
     const int words = (int)((job.src.pitch + 3) / 4);
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
-    const int64_t col_blocks = (words + 127) / 128;
     const bool aligned_out = (job.src.pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.out % 4 == 0);
+    const int64_t col_blocks = aligned_out ? (words + 127) / 128 : (words + 123) / 124;   // unaligned: 4 warps x 31 columns
     static int per_sm[2] = {0, 0};                                // resident blocks per SM of the two variants
     if (per_sm[aligned_out] == 0) {
         int n = 0;
