@@ -193,7 +193,11 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     const int64_t src_lo = job.src.band_y0, src_hi = job.src.band_y1;
     const uint8_t* rp;                       // pointer of the row most recently loaded
     int64_t rp_y;
+    // The last input row any output of this tile reads.  The load pipeline runs three rows ahead of the stencil: past
+    // this row it reloads the same row instead (d_below holds only the rows the stencil needs, not the prefetch).
+    const int64_t y_need_max = (Y1 < H - 1) ? Y1 : H - 1;
     auto next_row = [&](int64_t y) {         // rows are requested in increasing order
+        if (y > y_need_max) y = y_need_max;
         if (y > src_lo && y < src_hi && y < H && rp_y == y - 1) rp += pitch;
         else rp = job.src.row(clamp64(y, 0, H - 1), img);
         rp_y = y;

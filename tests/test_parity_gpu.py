@@ -368,3 +368,35 @@ def test_in_place_calls(c, path):
         xout = buf[1024:1024 + n].view(h, w, c)
         call(xin, xout)
         _check(kind, xout.cpu().numpy(), want, kind + " overlapping")
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_bands_with_exactly_the_promised_halo_rows(c, path):
+    """d_above / d_below hold rows_above / rows_below rows and not one more (gip_b200.h): one-row bands whose
+    neighbours are separate, exactly sized device buffers.  (The Sobel load pipeline used to prefetch past them.)"""
+    import torch
+    L = _lib.load()
+    h, w = 64, 1924
+    img = synth.uniform(h, w, c, seed=5 + c)
+    pitch = w * c
+    cuts = [0, 30, 31, 32, 33, 64]
+    stream = torch.cuda.current_stream().cuda_stream
+    for kind, r in (("sobel", 1), ("box", 1), ("gaussian", 1)):
+        bands = [torch.from_numpy(img[a:b].copy()).cuda() for a, b in zip(cuts[:-1], cuts[1:])]
+        outs = [torch.zeros_like(t) for t in bands]
+        for i, (y0, y1) in enumerate(zip(cuts[:-1], cuts[1:])):
+            ra, rb = min(r, y0), min(r, h - y1)
+            above = bands[i - 1].data_ptr() + (bands[i - 1].shape[0] - ra) * pitch if ra else None
+            below = bands[i + 1].data_ptr() if rb else None
+            args = (bands[i].data_ptr(), above, below, outs[i].data_ptr(), w, h, c, y0, y1 - y0, ra, rb)
+            if kind == "sobel":
+                rc = L.gip_sobel_band(*args, 2, stream)
+            elif kind == "box":
+                rc = L.gip_box_blur_band(*args, r, 1, stream)
+            else:
+                rc = L.gip_gaussian_blur_band(*args, 1.0, r, 1, stream)
+            assert rc == 0
+        torch.cuda.synchronize()
+        got = np.concatenate([t.cpu().numpy() for t in outs], axis=0)
+        want = {"sobel": lambda: O.sobel(img, 2), "box": lambda: O.box_blur(img, 1), "gaussian": lambda: O.gaussian_blur(img, 1.0, 1)}[kind]()
+        _check(kind, got, want, kind + " one-row bands")
