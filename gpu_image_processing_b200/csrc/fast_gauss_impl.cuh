@@ -239,7 +239,7 @@ template <int R> struct VCfg {
 };
 
 template <int R, bool kAlignedOut>
-__global__ void __launch_bounds__(128, (R <= 4 && kAlignedOut) ? 6 : 1)
+__global__ void __launch_bounds__(128, (R <= 4 && kAlignedOut) ? 5 : 1)
 gip_gauss_v(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, int64_t ty0, int64_t ty1,
             int64_t img0, int nbands, int band_rows, int words, int64_t tpitch) {
     constexpr int R2 = VCfg<R>::R2;
