@@ -5,12 +5,15 @@
 // and converts 9 pixels to gray for every output pixel; here every input byte is read once and every
 // gray value is computed once.
 //
-// A warp owns a strip of 120 output pixels and marches down a band of rows.  Lane l holds 4 consecutive
-// pixels (12 / 16 / 4 bytes for RGB / RGBA / gray, loaded as 32-bit words: 384 contiguous bytes per warp
-// row); lanes 0 and 31 are halo lanes whose pixels are only read by their neighbours.  The gray values of
-// the previous two rows stay in registers; x+-1 neighbours come from __shfl_up/down.  No shared memory, no
-// block barrier.  Arithmetic is packed float32x2 (FADD2/FMUL2/FFMA2: pixels 0,2 and 1,3 of a lane form
-// the pairs) and reproduces the reference's rounding sequence exactly:
+// A warp owns a strip of 240 output pixels and marches down a band of rows.  Lane l holds 8 consecutive
+// pixels of a row (24 / 32 / 8 bytes for RGB / RGBA / gray, loaded as 8- or 16-byte vectors: a warp row is
+// 768 / 1024 / 256 contiguous bytes); lanes 0 and 31 are halo lanes whose pixels are only read by their
+// neighbours.  The gray values of the previous two rows stay in registers; pixel -1 and pixel 8 of a
+// lane come from __shfl_up/down.  No shared memory, no block barrier.
+// Arithmetic is packed float32x2 (FADD2/FMUL2/FFMA2).  The two halves of a pair are pixels m and m+4
+// of the lane, so the pairs (left, centre, right) of an output pair are other whole pairs of the same
+// row -- nothing is re-packed except the two pairs that hold a shuffled neighbour.  The sequence of
+// roundings is the reference's:
 //   u8 -> float     PRMT into the mantissa of 2^23, minus 2^23 (exact)
 //   gray            fma(B, .114f, fma(R, .299f, G * .587f))            (:1245, order read off the reference SASS)
 //   level 2         gray := (float)(uchar)(gray + 0.5f)                  (:1443-1444)
@@ -19,7 +22,10 @@
 //                   (MUFU.RSQ, x*r, r/2, fma(-s,s,x), fma(d,h,s)); fminf(., 255); +0.5f; truncate (:1303-1305)
 //   borders         pixels with x or y on the image edge are 0 in every channel (:1164-1176)
 // The edge value is replicated into every channel, alpha included (:1311-1313).
+// Warps whose 32 lanes all lie inside the row (every strip but the first and the last one or two of a
+// row) run a path without per-word offsets, masks and store predicates.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "device_utils.cuh"
 
@@ -28,80 +34,90 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
-constexpr int kStripPixels = 120;       // 30 producing lanes x 4 pixels
+constexpr int kLanePixels = 8;
+constexpr int kStripPixels = 30 * kLanePixels;       // 30 producing lanes
 
 struct SobelTiling {
     int strips, bands, band_rows;
     long long tiles;
 };
 
-struct GrayRow {          // gray of this lane's pixels (0,2), (1,3) and the shifted pairs (-1,1), (2,4)
-    uint64_t A, B, PL, PR;
-    // integer gray only (level 2, or gray input): right - left and left + 2*centre + right of this row, for the
-    // pixel pairs (0,2) and (1,3)
-    uint64_t DA, DB, SA, SB;
-};
-
 template <int C>
-struct RowWords { uint32_t w[C]; };
+struct RowWords { uint32_t w[2 * C]; };              // the 8 pixels of one lane, one row
 
-// `off[k]` are in-row byte offsets made safe once per lane (words outside the row read offset 0:
-// their pixels only feed border outputs, which are zero).
-template <int C, bool kVec16>
-__device__ __forceinline__ RowWords<C> load_words(const uint8_t* row, const int (&off)[C]) {
-    RowWords<C> r;
-    if (C == 4 && kVec16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + off[0]));
-        r.w[0] = v.x; r.w[1 % C] = v.y; r.w[2 % C] = v.z; r.w[3 % C] = v.w;
+// Gray values of a row as the stencil wants them.  Float gray (level 1 colour): the pairs themselves.
+// Integer gray (level 2 rounds gray to u8, :1443-1444; gray input is u8 already): every partial sum of the
+// reference's gx / gy is an integer below 2^24, so the float32 adds are exact in ANY order and the stencil can be
+// taken apart: gx = D(top) + 2 D(mid) + D(bottom) with D = right - left, gy = S(bottom) - S(top) with
+// S = left + 2 centre + right, D and S computed once per row.  Same bits as the reference, 6 instead of 11 adds.
+template <bool kInt> struct GrayRow;
+template <> struct GrayRow<false> { uint64_t Q[4], L0, R3; };   // Q[m] = pixels (m, m+4); L0 = (-1, 3); R3 = (4, 8)
+template <> struct GrayRow<true> { uint64_t D[4], S[4]; };
+
+template <int VB>
+__device__ __forceinline__ void load_vec(uint32_t* dst, const uint8_t* p) {
+    if (VB == 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    } else if (VB == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        dst[0] = v.x; dst[1] = v.y;
     } else {
-#pragma unroll
-        for (int k = 0; k < C; k++) r.w[k] = __ldg(reinterpret_cast<const uint32_t*>(row + off[k]));
+        dst[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
     }
-    return r;
+}
+__device__ __forceinline__ void stg64_stream(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+template <int VB>
+__device__ __forceinline__ void store_vec(uint8_t* p, const uint32_t* src) {
+    if (VB == 16) stg128_stream(p, make_uint4(src[0], src[1], src[2], src[3]));
+    else if (VB == 8) stg64_stream(p, src[0], src[1]);
+    else stg32_stream(p, src[0]);
 }
 
-// byte `idx` (0..4C-1) of the lane's words as the float bit pattern 2^23 + byte
+// byte `idx` (0..8C-1) of the lane's words as the float bit pattern 2^23 + byte
 template <int C>
 __device__ __forceinline__ uint32_t biased_byte(const RowWords<C>& r, int idx) {
     return __byte_perm(r.w[idx >> 2], 0x4B000000u, 0x7540 | (idx & 3));
 }
 
 template <int C, bool kU8>
-__device__ __forceinline__ GrayRow make_gray(const RowWords<C>& r, int lane) {
+__device__ __forceinline__ GrayRow<kU8 || C == 1> make_gray(const RowWords<C>& r) {
+    constexpr bool kInt = kU8 || C == 1;
     const uint64_t kNeg23 = splat_f2(-8388608.0f);
-    uint64_t A, B;
-    if (C == 1) {
-        A = add_rn_x2(pack_f2(biased_byte<C>(r, 0), biased_byte<C>(r, 2)), kNeg23);
-        B = add_rn_x2(pack_f2(biased_byte<C>(r, 1), biased_byte<C>(r, 3)), kNeg23);
-    } else {
-        // pixel j: R = byte C*j, G = C*j+1, B = C*j+2
-        const uint64_t RA = add_rn_x2(pack_f2(biased_byte<C>(r, 0), biased_byte<C>(r, 2 * C)), kNeg23);
-        const uint64_t GA = add_rn_x2(pack_f2(biased_byte<C>(r, 1), biased_byte<C>(r, 2 * C + 1)), kNeg23);
-        const uint64_t BA = add_rn_x2(pack_f2(biased_byte<C>(r, 2), biased_byte<C>(r, 2 * C + 2)), kNeg23);
-        const uint64_t RB = add_rn_x2(pack_f2(biased_byte<C>(r, C), biased_byte<C>(r, 3 * C)), kNeg23);
-        const uint64_t GB = add_rn_x2(pack_f2(biased_byte<C>(r, C + 1), biased_byte<C>(r, 3 * C + 1)), kNeg23);
-        const uint64_t BB = add_rn_x2(pack_f2(biased_byte<C>(r, C + 2), biased_byte<C>(r, 3 * C + 2)), kNeg23);
-        const uint64_t kR = splat_f2(0.299f), kG = splat_f2(0.587f), kB = splat_f2(0.114f);
-        A = fma_rn_x2(BA, kB, fma_rn_x2(RA, kR, mul_rn_x2(GA, kG)));
-        B = fma_rn_x2(BB, kB, fma_rn_x2(RB, kR, mul_rn_x2(GB, kG)));
-        if (kU8) {           // (float)(uchar)(gray + 0.5f): add, truncate on the 2^23 grid, remove the bias
-            const uint64_t kHalf = splat_f2(0.5f), k23 = splat_f2(8388608.0f);
-            A = add_rn_x2(add_rz_x2(add_rn_x2(A, kHalf), k23), kNeg23);
-            B = add_rn_x2(add_rz_x2(add_rn_x2(B, kHalf), k23), kNeg23);
+    uint64_t Q[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        if (C == 1) {
+            Q[m] = add_rn_x2(pack_f2(biased_byte<C>(r, m), biased_byte<C>(r, m + 4)), kNeg23);
+        } else {
+            // pixel j: R = byte C*j, G = C*j+1, B = C*j+2
+            const uint64_t Rv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m), biased_byte<C>(r, C * (m + 4))), kNeg23);
+            const uint64_t Gv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m + 1), biased_byte<C>(r, C * (m + 4) + 1)), kNeg23);
+            const uint64_t Bv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m + 2), biased_byte<C>(r, C * (m + 4) + 2)), kNeg23);
+            uint64_t g = fma_rn_x2(Bv, splat_f2(0.114f), fma_rn_x2(Rv, splat_f2(0.299f), mul_rn_x2(Gv, splat_f2(0.587f))));
+            if (kU8)             // (float)(uchar)(gray + 0.5f): add, truncate on the 2^23 grid, remove the bias
+                g = add_rn_x2(add_rz_x2(add_rn_x2(g, splat_f2(0.5f)), splat_f2(8388608.0f)), kNeg23);
+            Q[m] = g;
         }
     }
-    GrayRow g;
-    g.A = A; g.B = B;
-    const uint32_t left = __shfl_up_sync(0xffffffffu, hi_f2(B), 1);     // pixel 3 of lane-1 == pixel -1
-    const uint32_t right = __shfl_down_sync(0xffffffffu, lo_f2(A), 1);  // pixel 0 of lane+1 == pixel 4
-    g.PL = pack_f2(left, lo_f2(B));      // pixels (-1, 1)
-    g.PR = pack_f2(hi_f2(A), right);     // pixels ( 2, 4)
-    if (kU8 || C == 1) {
-        const uint64_t kP2 = splat_f2(2.0f);
-        g.DA = sub_rn_x2(B, g.PL);       g.SA = add_rn_x2(fma_rn_x2(A, kP2, g.PL), B);
-        g.DB = sub_rn_x2(g.PR, A);       g.SB = add_rn_x2(fma_rn_x2(B, kP2, A), g.PR);
+    const uint32_t left = __shfl_up_sync(0xffffffffu, hi_f2(Q[3]), 1);      // pixel 7 of lane-1 == pixel -1
+    const uint32_t right = __shfl_down_sync(0xffffffffu, lo_f2(Q[0]), 1);   // pixel 0 of lane+1 == pixel 8
+    const uint64_t L0 = pack_f2(left, lo_f2(Q[3]));       // pixels (-1, 3)
+    const uint64_t R3 = pack_f2(hi_f2(Q[0]), right);      // pixels ( 4, 8)
+    GrayRow<kInt> g;
+    if constexpr (kInt) {
+        const uint64_t k2 = splat_f2(2.0f);
+        g.D[0] = sub_rn_x2(Q[1], L0);   g.S[0] = add_rn_x2(fma_rn_x2(Q[0], k2, L0), Q[1]);
+        g.D[1] = sub_rn_x2(Q[2], Q[0]); g.S[1] = add_rn_x2(fma_rn_x2(Q[1], k2, Q[0]), Q[2]);
+        g.D[2] = sub_rn_x2(Q[3], Q[1]); g.S[2] = add_rn_x2(fma_rn_x2(Q[2], k2, Q[1]), Q[3]);
+        g.D[3] = sub_rn_x2(R3, Q[2]);   g.S[3] = add_rn_x2(fma_rn_x2(Q[3], k2, Q[2]), R3);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) g.Q[m] = Q[m];
+        g.L0 = L0; g.R3 = R3;
     }
-    (void)lane;
     return g;
 }
 
@@ -121,28 +137,26 @@ __device__ __forceinline__ uint64_t magnitude_pair(uint64_t gx, uint64_t gy) {
     return add_rz_x2(add_rn_x2(s, splat_f2(0.5f)), splat_f2(8388608.0f));
 }
 
-// Sobel magnitude of two pixels, as float bit patterns whose low byte is the rounded u8.
+// Sobel magnitude of two pixels, as float bit patterns whose low byte is the rounded u8.  The reference adds the taps
+// in row-major order with one rounding each (:1246-1299):
+//   gx = ((((-TL + TR) - 2 ML) + 2 MR) - BL) + BR        gy = ((((-TL - 2 TC) - TR) + BL) + 2 BC) + BR
+// 0 - TL is exact and round-to-nearest is symmetric, so -TL + TR == TR - TL and (-TL - 2 TC) - TR == -((TL + 2 TC) + TR)
+// bit for bit: the negations are carried instead of computed (10 operations instead of 11).
 __device__ __forceinline__ uint64_t sobel_pair(uint64_t TL, uint64_t TC, uint64_t TR, uint64_t ML, uint64_t MR,
                                                uint64_t BL, uint64_t BC, uint64_t BR) {
-    const uint64_t kM2 = splat_f2(-2.0f), kP2 = splat_f2(2.0f), kZero = splat_f2(0.0f);
-    uint64_t gx = sub_rn_x2(kZero, TL);             // -TL
-    uint64_t gy = fma_rn_x2(TC, kM2, gx);           // -TL - 2TC        (one rounding)
-    gx = add_rn_x2(gx, TR);
-    gy = sub_rn_x2(gy, TR);
+    const uint64_t kM2 = splat_f2(-2.0f), kP2 = splat_f2(2.0f);
+    uint64_t gx = sub_rn_x2(TR, TL);
+    uint64_t ngy = fma_rn_x2(TC, kP2, TL);          // -(gy so far)
     gx = fma_rn_x2(ML, kM2, gx);
+    ngy = add_rn_x2(ngy, TR);
     gx = fma_rn_x2(MR, kP2, gx);
+    uint64_t gy = sub_rn_x2(BL, ngy);
     gx = sub_rn_x2(gx, BL);
-    gy = add_rn_x2(gy, BL);
     gy = fma_rn_x2(BC, kP2, gy);
     gx = add_rn_x2(gx, BR);
     gy = add_rn_x2(gy, BR);
     return magnitude_pair(gx, gy);
 }
-
-// Integer gray values (level 2 rounds gray to u8, :1443-1444; gray input is u8 already): every partial sum of the
-// reference's gx / gy is an integer below 2^24, so the float32 adds are exact in ANY order and the stencil can be
-// taken apart: gx = D(top) + 2 D(mid) + D(bottom) with D = right - left, gy = S(bottom) - S(top) with
-// S = left + 2 centre + right, D and S computed once per row.  Same bits as the reference, 6 instead of 11 adds.
 __device__ __forceinline__ uint64_t sobel_pair_int(uint64_t Dt, uint64_t Dm, uint64_t Db, uint64_t St, uint64_t Sb) {
     const uint64_t gx = add_rn_x2(fma_rn_x2(Dm, splat_f2(2.0f), Dt), Db);
     const uint64_t gy = sub_rn_x2(Sb, St);
@@ -150,9 +164,37 @@ __device__ __forceinline__ uint64_t sobel_pair_int(uint64_t Dt, uint64_t Dm, uin
 }
 __device__ __forceinline__ uint32_t clamp255(uint32_t z) { return min(z, 0x4B0000FFu); }
 
-template <int C, bool kU8, bool kVec16>
-__global__ void __launch_bounds__(kThreads, 3)
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// Output rows of colour images leave through a per-warp slab of shared memory: a lane's 24 (RGB) or 32 (RGBA) bytes
+// are written to the slab, and the warp stores the slab with consecutive lanes on consecutive 8- / 16-byte chunks, so
+// that every store instruction writes whole 32-byte sectors (lane-strided stores write every sector in 3 pieces: the
+// round-1 capture showed 9.8 M L2 write sectors for a 3.1 M-sector image).
+template <int C, int VB> struct Slab {
+    static constexpr bool kUse = (C == 3 && VB == 8) || (C == 4 && VB == 16);
+    static constexpr int kBytes = kUse ? 32 * 8 * C : 0;                       // one row of one warp
+};
+
+template <int C, bool kU8, int VB>
+__global__ void __launch_bounds__(kThreads, 2)
 gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTiling tl) {
+    constexpr bool kInt = kU8 || C == 1;
+    constexpr bool kSlab = Slab<C, VB>::kUse;
+    __shared__ __align__(16) uint8_t slab_mem[kSlab ? 2 * Slab<C, VB>::kBytes * kWarpsPerBlock : 16];
+    const uint32_t slab0 = smem_addr(slab_mem) + (uint32_t)((threadIdx.x >> 5) * 2 * Slab<C, VB>::kBytes);
+    constexpr int NW = 2 * C;                 // words per lane and row
+    constexpr int NCH = 8 * C / VB;           // vector chunks per lane and row
+    constexpr int WPC = VB / 4;               // words per chunk
     const int lane = threadIdx.x & 31;
     long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (tile >= tl.tiles) return;
@@ -164,158 +206,196 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     const int64_t Y1 = (Y0 + tl.band_rows < job.src.band_y1) ? Y0 + tl.band_rows : job.src.band_y1;
     if (Y0 >= Y1) return;
 
-    const int64_t x0 = (int64_t)strip * kStripPixels - 4 + 4 * lane;    // first pixel of this lane
+    const int64_t x0 = (int64_t)strip * kStripPixels - kLanePixels + kLanePixels * lane;    // first pixel of this lane
     const int64_t boff = x0 * C;
     const bool stores = lane >= 1 && lane <= 30;
-    // per-word load offsets, store predicates and border masks (x == 0, x == W-1 and x >= W give 0 / no store)
-    int off[C];
-    bool wvalid[C];
-    uint32_t wmask[C];
-#pragma unroll
-    for (int k = 0; k < C; k++) {
-        const int64_t o = boff + 4 * k;
-        const bool inside = o >= 0 && o + 4 <= pitch;
-        off[k] = inside ? (int)o : 0;
-        wvalid[k] = stores && inside;
-        uint32_t m = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int64_t px = (o + b) / C;
-            if (px >= 1 && px <= W - 2) m |= 0xFFu << (8 * b);
-        }
-        wmask[k] = m;
-    }
-    if (C == 4 && kVec16 && !(boff >= 0 && boff + 16 <= pitch)) off[0] = 0;
+    const bool lane_inside = boff >= 0 && boff + 8 * C <= pitch;
+    const bool edge = !__all_sync(0xffffffffu, lane_inside);    // first / last strips of a row: offsets, masks, predicates
 
-    // Row pointers advance by `pitch` inside the band's own rows and are recomputed at the seams
-    // (image top / bottom clamp, rows owned by the neighbours above / below).
+    // Input rows Y0-1 .. Y1 of the tile, requested in order.  Rows Y0 .. Y1-1 are the band's own memory (one pointer,
+    // advanced by `pitch`); only the first and the last row can lie across a seam (image top / bottom clamp, rows owned
+    // by the neighbours above / below), so their pointers are computed once.  The load pipeline runs three rows ahead of
+    // the stencil: past the last row any output needs it re-reads that row (d_below holds only the rows the stencil
+    // needs, not the prefetch).
     const int nrows = (int)(Y1 - Y0);
-    const int64_t src_lo = job.src.band_y0, src_hi = job.src.band_y1;
-    const uint8_t* rp;                       // pointer of the row most recently loaded
-    int64_t rp_y;
-    // The last input row any output of this tile reads.  The load pipeline runs three rows ahead of the stencil: past
-    // this row it reloads the same row instead (d_below holds only the rows the stencil needs, not the prefetch).
-    const int64_t y_need_max = (Y1 < H - 1) ? Y1 : H - 1;
-    auto next_row = [&](int64_t y) {         // rows are requested in increasing order
-        if (y > y_need_max) y = y_need_max;
-        if (y > src_lo && y < src_hi && y < H && rp_y == y - 1) rp += pitch;
-        else rp = job.src.row(clamp64(y, 0, H - 1), img);
-        rp_y = y;
+    const uint8_t* const p_first = job.src.row(clamp64(Y0 - 1, 0, H - 1), img);
+    const uint8_t* const p_last = job.src.row(clamp64(Y1, 0, H - 1), img);
+    const uint8_t* rp = job.src.band + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch - pitch;   // "row Y0-1" of the band's memory
+    int t_next = 0;                          // the next row of the band's own memory, relative to Y0
+    auto next_own_row = [&]() {              // rows Y0, Y0+1, ... ; from Y1 on: the last row, again and again
+        rp = (t_next < nrows) ? rp + pitch : p_last;
+        t_next++;
         return rp;
     };
     uint8_t* out = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + boff;
     const int y_first = (int)Y0;             // image rows fit 31 bits here (checked on the host)
     const int y_last_interior = (int)(H - 2);
 
-    auto emit = [&](const GrayRow& T, const GrayRow& M, const GrayRow& Bt, int y) {
-        uint32_t w[C];
-        if (y >= 1 && y <= y_last_interior) {
-            uint64_t zA, zB;                                                                  // pixels 0, 2 and 1, 3
-            if (kU8 || C == 1) {
-                zA = sobel_pair_int(T.DA, M.DA, Bt.DA, T.SA, Bt.SA);
-                zB = sobel_pair_int(T.DB, M.DB, Bt.DB, T.SB, Bt.SB);
-            } else {
-                zA = sobel_pair(T.PL, T.A, T.B, M.PL, M.B, Bt.PL, Bt.A, Bt.B);
-                zB = sobel_pair(T.A, T.B, T.PR, M.A, M.PR, Bt.A, Bt.B, Bt.PR);
-            }
-            const uint32_t z0 = clamp255(lo_f2(zA)), z2 = clamp255(hi_f2(zA));
-            const uint32_t z1 = clamp255(lo_f2(zB)), z3 = clamp255(hi_f2(zB));
-            if (C == 1) {
-                w[0] = __byte_perm(__byte_perm(z0, z1, 0x4040), __byte_perm(z2, z3, 0x4040), 0x5410);
-            } else if (C == 3) {
-                w[0] = __byte_perm(z0, z1, 0x4000); w[1 % C] = __byte_perm(z1, z2, 0x4400); w[2 % C] = __byte_perm(z2, z3, 0x4440);
-            } else {
-                w[0] = __byte_perm(z0, z0, 0x0000); w[1 % C] = __byte_perm(z1, z1, 0x0000);
-                w[2 % C] = __byte_perm(z2, z2, 0x0000); w[3 % C] = __byte_perm(z3, z3, 0x0000);
-            }
+    // magnitudes of output row y (rows T, M, B = y-1, y, y+1) -> z[j] = float bits whose low byte is pixel j
+    auto stencil = [&](const GrayRow<kInt>& T, const GrayRow<kInt>& M, const GrayRow<kInt>& Bt, uint32_t (&z)[8]) {
+        uint64_t zz[4];
+        if constexpr (kInt) {
 #pragma unroll
-            for (int k = 0; k < C; k++) w[k] &= wmask[k];
+            for (int m = 0; m < 4; m++) zz[m] = sobel_pair_int(T.D[m], M.D[m], Bt.D[m], T.S[m], Bt.S[m]);
+        } else {
+            zz[0] = sobel_pair(T.L0, T.Q[0], T.Q[1], M.L0, M.Q[1], Bt.L0, Bt.Q[0], Bt.Q[1]);
+            zz[1] = sobel_pair(T.Q[0], T.Q[1], T.Q[2], M.Q[0], M.Q[2], Bt.Q[0], Bt.Q[1], Bt.Q[2]);
+            zz[2] = sobel_pair(T.Q[1], T.Q[2], T.Q[3], M.Q[1], M.Q[3], Bt.Q[1], Bt.Q[2], Bt.Q[3]);
+            zz[3] = sobel_pair(T.Q[2], T.Q[3], T.R3, M.Q[2], M.R3, Bt.Q[2], Bt.Q[3], Bt.R3);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) { z[m] = clamp255(lo_f2(zz[m])); z[m + 4] = clamp255(hi_f2(zz[m])); }
+    };
+    // the lane's output words: every channel of pixel j is z[j]
+    auto pack = [&](const uint32_t (&z)[8], uint32_t (&w)[NW]) {
+        if constexpr (C == 1) {
+            w[0] = __byte_perm(__byte_perm(z[0], z[1], 0x4040), __byte_perm(z[2], z[3], 0x4040), 0x5410);
+            w[1] = __byte_perm(__byte_perm(z[4], z[5], 0x4040), __byte_perm(z[6], z[7], 0x4040), 0x5410);
+        } else if constexpr (C == 3) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                w[3 * q] = __byte_perm(z[4 * q], z[4 * q + 1], 0x4000);
+                w[3 * q + 1] = __byte_perm(z[4 * q + 1], z[4 * q + 2], 0x4400);
+                w[3 * q + 2] = __byte_perm(z[4 * q + 2], z[4 * q + 3], 0x4440);
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < C; k++) w[k] = 0;
+            for (int j = 0; j < 8; j++) w[j] = __byte_perm(z[j], z[j], 0x0000);
         }
-        if (C == 4 && kVec16) {
-            if (wvalid[0]) stg128_stream(out, make_uint4(w[0], w[1 % C], w[2 % C], w[3 % C]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; k++)
-                if (wvalid[k]) stg32_stream(out + 4 * k, w[k]);
-        }
-        out += pitch;
     };
 
-    // rows Y0-1 and Y0 prime the pipeline; the words of the next THREE rows are always in flight (three word
-    // buffers rotate with the three gray rows, so nothing is copied between iterations)
-    rp_y = Y0 - 3;
-    GrayRow R0 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0 - 1), off), lane);
-    GrayRow R1 = make_gray<C, kU8>(load_words<C, kVec16>(next_row(Y0), off), lane);
-    GrayRow R2;
-    RowWords<C> W0 = load_words<C, kVec16>(next_row(Y0 + 1), off);
-    RowWords<C> W1 = load_words<C, kVec16>(next_row(Y0 + 2), off);
-    RowWords<C> W2 = load_words<C, kVec16>(next_row(Y0 + 3), off);
-    for (int i = 0; i < nrows; i += 3) {
-        const int y = y_first + i;
-        // output row y needs rows y-1 (R0), y (R1), y+1 (W0 -> R2)
-        R2 = make_gray<C, kU8>(W0, lane);
-        W0 = load_words<C, kVec16>(next_row((int64_t)y + 4), off);
-        emit(R0, R1, R2, y);
-        if (i + 1 >= nrows) break;
-        R0 = make_gray<C, kU8>(W1, lane);
-        W1 = load_words<C, kVec16>(next_row((int64_t)y + 5), off);
-        emit(R1, R2, R0, y + 1);
-        if (i + 2 >= nrows) break;
-        R1 = make_gray<C, kU8>(W2, lane);
-        W2 = load_words<C, kVec16>(next_row((int64_t)y + 6), off);
-        emit(R2, R0, R1, y + 2);
-    }
+    auto march = [&](auto edge_tag) {
+        constexpr bool kEdge = decltype(edge_tag)::value;
+        // kEdge: per-chunk load offsets made safe once per lane (chunks outside the row read offset 0: their pixels
+        // only feed border outputs, which are zero), store predicates and border masks (x == 0, x == W-1, x >= W).
+        int coff[NCH];
+        bool cvalid[NCH];
+        uint32_t wmask[NW];
+        if (kEdge) {
+#pragma unroll
+            for (int k = 0; k < NCH; k++) {
+                const int64_t o = boff + VB * k;
+                const bool inside = o >= 0 && o + VB <= pitch;
+                coff[k] = inside ? (int)o : 0;
+                cvalid[k] = stores && inside;
+            }
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                uint32_t m = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int64_t ob = boff + 4 * k + b;
+                    if (ob >= 0) {
+                        const int64_t px = ob / C;
+                        if (px >= 1 && px <= W - 2) m |= 0xFFu << (8 * b);
+                    }
+                }
+                wmask[k] = m;
+            }
+        }
+        auto load = [&](const uint8_t* row) {
+            RowWords<C> r;
+#pragma unroll
+            for (int k = 0; k < NCH; k++) load_vec<VB>(&r.w[WPC * k], kEdge ? row + coff[k] : row + boff + VB * k);
+            return r;
+        };
+        auto emit = [&](const GrayRow<kInt>& T, const GrayRow<kInt>& M, const GrayRow<kInt>& Bt, int y) {
+            uint32_t w[NW];
+            if (y >= 1 && y <= y_last_interior) {
+                uint32_t z[8];
+                stencil(T, M, Bt, z);
+                pack(z, w);
+                if (kEdge) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) w[k] &= wmask[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NW; k++) w[k] = 0;
+            }
+            if constexpr (kSlab && !kEdge) {
+                // out points at the lane's own bytes: the warp's segment starts 8*C*lane bytes before it
+                const uint32_t slab = slab0 + (uint32_t)((y & 1) * Slab<C, VB>::kBytes);
+                if constexpr (C == 3) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) sts64(slab + 24 * lane + 8 * k, w[2 * k], w[2 * k + 1]);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const int c = lane + 32 * j;                 // 8-byte chunk of the segment; its owner is lane c / 3
+                        const uint2 v = lds64(slab + 8 * c);
+                        if (c >= 3 && c < 93) stg64_stream(out - 24 * lane + 8 * c, v.x, v.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const int c = 2 * lane + k;                  // 16-byte chunk; slot = c ^ bit 3 of c: conflict-free both ways
+                        sts128(slab + 16 * (c ^ ((c >> 3) & 1)), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int c = lane + 32 * j;                 // owner is lane c / 2
+                        const uint4 v = lds128(slab + 16 * (c ^ ((c >> 3) & 1)));
+                        if (c >= 2 && c < 62) stg128_stream(out - 32 * lane + 16 * c, v);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NCH; k++)
+                    if (kEdge ? cvalid[k] : stores) store_vec<VB>(out + VB * k, &w[WPC * k]);
+            }
+            out += pitch;
+        };
+
+        // rows Y0-1 and Y0 prime the pipeline; the words of the next THREE rows are always in flight (three word
+        // buffers rotate with the three gray rows, so nothing is copied between iterations)
+        GrayRow<kInt> R0 = make_gray<C, kU8>(load(p_first));
+        GrayRow<kInt> R1 = make_gray<C, kU8>(load(next_own_row()));
+        GrayRow<kInt> R2;
+        RowWords<C> W0 = load(next_own_row());
+        RowWords<C> W1 = load(next_own_row());
+        RowWords<C> W2 = load(next_own_row());
+        for (int i = 0; i < nrows; i += 3) {
+            const int y = y_first + i;
+            // output row y needs rows y-1 (R0), y (R1), y+1 (W0 -> R2)
+            R2 = make_gray<C, kU8>(W0);
+            W0 = load(next_own_row());
+            emit(R0, R1, R2, y);
+            if (i + 1 >= nrows) break;
+            R0 = make_gray<C, kU8>(W1);
+            W1 = load(next_own_row());
+            emit(R1, R2, R0, y + 1);
+            if (i + 2 >= nrows) break;
+            R1 = make_gray<C, kU8>(W2);
+            W2 = load(next_own_row());
+            emit(R2, R0, R1, y + 2);
+        }
+    };
+    if (edge) march(std::true_type{});
+    else march(std::false_type{});
 }
 
-int g_num_sms = 0;
-
-template <int C, bool kU8, bool kVec16>
-cudaError_t launch(const Job& job, const SobelTiling& tl, cudaStream_t stream) {
-    const long long blocks = (tl.tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    gip_sobel_fused<C, kU8, kVec16><<<(unsigned)blocks, kThreads, 0, stream>>>(job, tl);
-    count_launch();
-    return cudaGetLastError();
-}
-
-template <int C>
-cudaError_t launch_c(const Job& job, const SobelTiling& tl, bool vec16, cudaStream_t stream) {
-    if (job.sobel_u8_gray && C != 1)
-        return vec16 ? launch<C, true, true>(job, tl, stream) : launch<C, true, false>(job, tl, stream);
-    return vec16 ? launch<C, false, true>(job, tl, stream) : launch<C, false, false>(job, tl, stream);
-}
-
-}  // namespace
-
-cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled) {
-    *handled = false;
-    const int C = job.channels;
-    const int64_t pitch = job.src.pitch;
-    // 32-bit word loads/stores: every row must start on a 4-byte boundary
-    const bool aligned4 = (pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.src.band % 4 == 0) &&
-                          ((uintptr_t)job.out % 4 == 0) && (!job.src.above || (uintptr_t)job.src.above % 4 == 0) &&
-                          (!job.src.below || (uintptr_t)job.src.below % 4 == 0);
-    if (!aligned4) return cudaSuccess;               // general path
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
+template <int C, bool kU8, int VB>
+cudaError_t launch(const Job& job, SobelTiling tl, int64_t per_band, int64_t rows, cudaStream_t stream, bool* handled) {
+    // Resident warps per SM of this instantiation on the current device (the attribute is per device).
+    static int per_sm_cache[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    int per_sm = per_sm_cache[dev];
+    if (per_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gip_sobel_fused<C, kU8, VB>, kThreads, 0);
         if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        per_sm_cache[dev] = per_sm;
     }
-    SobelTiling tl;
-    tl.strips = (int)((job.width + kStripPixels - 1) / kStripPixels);
-    const int64_t rows = job.src.band_y1 - job.src.band_y0;
-    if (rows > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
-    const int64_t per_band = (int64_t)tl.strips * job.batch;
     // Row bands: the band count with the smallest (waves of resident warps) x (rows a warp marches, its 2 halo rows and
-    // the 3-row load pipeline included).  24 warps are resident per SM (3 blocks of 8).  One full wave of tall bands
-    // for a single image (measured on 8K RGB, warps per SM: 24 -> 76.6 us, 25 -> 95.6, 48 -> 78.3, 64 -> 79.9);
-    // several finer waves for batches.
-    static const int warps_per_sm = [] { const char* e = getenv("GIP_SOBEL_WARPS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 24; }();
-    const int64_t resident = (int64_t)g_num_sms * warps_per_sm;
+    // the 3-row load pipeline included).  One full wave of tall bands for a single image, several finer waves for batches.
+    static const int warps_env = [] { const char* s = getenv("GIP_SOBEL_WARPS_PER_SM"); return s ? atoi(s) : 0; }();
+    const int warps_per_sm = warps_env > 0 ? warps_env : per_sm * kWarpsPerBlock;
+    const int64_t resident = (int64_t)num_sms() * warps_per_sm;
     int64_t max_bands = rows / 24; if (max_bands < 1) max_bands = 1;  // a band re-reads 2 halo rows
     if (max_bands > 1024) max_bands = 1024;
     int64_t bands = 1, best_cost = -1;
@@ -327,17 +407,44 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
     tl.bands = (int)bands;
     tl.band_rows = (int)((rows + bands - 1) / bands);
     tl.tiles = per_band * bands;
-    if ((tl.tiles + kWarpsPerBlock - 1) / kWarpsPerBlock > 0x7fffffffLL) return cudaSuccess;
-    const bool vec16 = (C == 4) && (pitch % 16 == 0) && (job.src.image_stride % 16 == 0) &&
-                       ((uintptr_t)job.src.band % 16 == 0) && ((uintptr_t)job.out % 16 == 0) &&
-                       (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
-                       (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
-    cudaError_t err;
-    if (C == 4)      err = launch_c<4>(job, tl, vec16, stream);
-    else if (C == 3) err = launch_c<3>(job, tl, false, stream);
-    else             err = launch_c<1>(job, tl, false, stream);
-    *handled = (err == cudaSuccess);
-    return err;
+    const long long blocks = (tl.tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL) return cudaSuccess;      // general path
+    gip_sobel_fused<C, kU8, VB><<<(unsigned)blocks, kThreads, 0, stream>>>(job, tl);
+    count_launch();
+    e = cudaGetLastError();
+    *handled = (e == cudaSuccess);
+    return e;
+}
+
+template <int C, int VB>
+cudaError_t launch_c(const Job& job, const SobelTiling& tl, int64_t per_band, int64_t rows, cudaStream_t stream, bool* handled) {
+    if (job.sobel_u8_gray && C != 1) return launch<C, true, VB>(job, tl, per_band, rows, stream, handled);
+    return launch<C, false, VB>(job, tl, per_band, rows, stream, handled);
+}
+
+}  // namespace
+
+cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    const int C = job.channels;
+    const int64_t pitch = job.src.pitch;
+    auto aligned = [&](int a) {
+        return (pitch % a == 0) && (job.src.image_stride % a == 0) && ((uintptr_t)job.src.band % a == 0) &&
+               ((uintptr_t)job.out % a == 0) && (!job.src.above || (uintptr_t)job.src.above % a == 0) &&
+               (!job.src.below || (uintptr_t)job.src.below % a == 0);
+    };
+    // vector loads/stores: every row must start on a 4-byte boundary at least
+    if (!aligned(4)) return cudaSuccess;             // general path
+    if (num_sms() <= 0) return cudaErrorInvalidDevice;
+    SobelTiling tl;
+    tl.strips = (int)((job.width + kStripPixels - 1) / kStripPixels);
+    const int64_t rows = job.src.band_y1 - job.src.band_y0;
+    if (rows > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
+    const int64_t per_band = (int64_t)tl.strips * job.batch;
+    if (per_band > (int64_t)1 << 40) return cudaSuccess;
+    if (C == 4) return aligned(16) ? launch_c<4, 16>(job, tl, per_band, rows, stream, handled) : launch_c<4, 4>(job, tl, per_band, rows, stream, handled);
+    if (C == 3) return aligned(8) ? launch_c<3, 8>(job, tl, per_band, rows, stream, handled) : launch_c<3, 4>(job, tl, per_band, rows, stream, handled);
+    return aligned(8) ? launch_c<1, 8>(job, tl, per_band, rows, stream, handled) : launch_c<1, 4>(job, tl, per_band, rows, stream, handled);
 }
 
 }  // namespace gip
