@@ -1,0 +1,321 @@
+// fused_gauss_impl.cuh -- single-kernel separable Gaussian blur for sm_100a, small radii, 16-byte aligned rows.
+//
+// Replaces gaussianBlur{Horizontal,Vertical}{Naive,Level2} AND the d_temp image between them
+// (/root/reference/cuda_lib/src/image_filters.cu:64-144, :159-347, :759-761): the horizontally filtered, u8-rounded
+// rows (the reference's intermediate, :102) live only in a shared-memory FIFO between the two passes, so every image
+// byte is read from HBM once and written once.
+//
+// A CTA (512 threads, one per SM) owns a column strip of 2048 output bytes and a band of rows and marches down the
+// band K = 16 rows per step.  It is warp-specialised:
+//   8 producer warps   stage input rows with 16-byte cp.async (two steps ahead, double-buffered) and run the H pass.
+//                      A warp filters two rows at once: the rows are the two lanes of the packed float32x2 operations
+//                      (FFMA2), so one issue slot does two taps and nothing is ever re-packed.  Lane l owns 64 output
+//                      bytes of both rows: it reads its 64 + 2*R*C input bytes with LDS.128, converts each byte once
+//                      (PRMT + I2FP, off the FP32 pipe) and accumulates every output in the reference's tap order
+//                      (:86-99: i = -R..R, one FMA per tap, first tap a multiply), rounds (:102) and writes the row
+//                      into the FIFO with STS.128.
+//   8 consumer warps   run the V pass one step behind.  A thread owns an 8-byte column group and keeps the 2R+1
+//                      partial sums of its columns in registers: a new FIFO row v updates  acc[t] = fma(v, w[t], acc[t-1])
+//                      for t = 2R..1, acc[0] = v * w[0]  (the rotation of the accumulators happens in the FMA's
+//                      destination: no register moves, no unrolling by 2R+1), the finished acc[2R] is rounded (:142) and
+//                      stored with STG.64; a warp writes 256 contiguous bytes.
+// Shared-memory rows are padded by one 16-byte chunk per 128 bytes, which makes the lane-strided (64-byte) LDS.128 /
+// STS.128 of the H pass conflict-free.
+// Arithmetic is bit-identical to the reference: float32 weights from the host (image_filters.cu:25-39), one fmaf per
+// tap in tap order, (uchar)(sum + 0.5f) == low mantissa byte of RZ(RN(sum + 0.5f) + 2^23).
+// The FP32 pipe is the roofline: 2 * ((2R+1) + 2) packed-lane operations per byte.
+#pragma once
+#include <cstring>
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace gip {
+namespace {
+
+constexpr int kFK = 16;                     // rows per step
+constexpr int kFProd = 8, kFCons = 8;       // producer / consumer warps
+constexpr int kFThreads = 32 * (kFProd + kFCons);
+constexpr int kFStrip = 2048;               // output bytes per strip (32 lanes x 64 bytes)
+constexpr int kFLane = 64;
+constexpr int kFRingRows = 2 * kFK;
+constexpr int kFRingPitch = kFStrip + kFStrip / 8;      // 2304: one pad chunk per 8 chunks
+
+// byte offset of byte `idx` of a row stored in the padded layout
+__host__ __device__ constexpr int padded_off(int idx) { return 16 * ((idx >> 4) + (idx >> 7)) + (idx & 15); }
+
+template <int R, int C> struct FCfg {
+    static constexpr int RC = R * C;
+    static constexpr int kPad = (RC + 15) & ~15;                    // bytes staged to the left of the strip
+    static constexpr int kDelta = kPad - RC;                        // a lane's first input byte inside its first chunk
+    static constexpr int kRowBytes = kPad + kFStrip + kPad;         // staged bytes per row
+    static constexpr int kRowChunks = kRowBytes / 16;
+    static constexpr int kStagePitch = 16 * (kRowChunks + (kRowChunks + 7) / 8);
+    static constexpr int kLaneChunks = (kDelta + kFLane + 2 * RC + 15) / 16;   // chunks a lane reads per row
+    static constexpr int kCopyIters = (kRowChunks + 31) / 32;
+    static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kFRingRows * kFRingPitch;
+    static_assert(kLaneChunks <= 8, "lane chunk addressing assumes at most 8 chunks");
+};
+
+struct FusedTiling {
+    int strips, bands, band_rows;
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void stg64_stream(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+// byte b (0..3) of word w -> float, exact (zero-extend with PRMT, I2FP on the integer side)
+__device__ __forceinline__ uint32_t byte_to_float_bits(uint32_t w, int b) {
+    return u2f_bits(__byte_perm(w, 0u, 0x4440 | b));
+}
+__device__ __forceinline__ uint64_t round_pair_f(uint64_t acc) {
+    return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
+}
+
+template <int R, int C>
+__global__ void __launch_bounds__(kFThreads, 1)
+gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTiling tl) {
+    using Cfg = FCfg<R, C>;
+    constexpr int RC = Cfg::RC, R2 = 2 * R + 1;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t pitch = job.src.pitch;
+
+    // ---- tile -> (image, band, strip)
+    unsigned tile = blockIdx.x;
+    const int strip = (int)(tile % (unsigned)tl.strips); tile /= (unsigned)tl.strips;
+    const int band = (int)(tile % (unsigned)tl.bands);
+    const int64_t img = tile / (unsigned)tl.bands;
+    const int64_t Y0 = job.src.band_y0 + (int64_t)band * tl.band_rows;
+    const int64_t Y1 = (Y0 + tl.band_rows < job.src.band_y1) ? Y0 + tl.band_rows : job.src.band_y1;
+    if (Y0 >= Y1) return;
+    const int64_t Ystart = Y0 - R;                   // first input row of the tile
+    const int nrows_in = (int)(Y1 - Y0) + 2 * R;
+    const int nsteps = (nrows_in + kFK - 1) / kFK;
+    const int64_t bxs = (int64_t)strip * kFStrip;    // first output byte of the strip
+    const int64_t A0 = bxs - Cfg::kPad;              // image-row byte position of staged byte 0 (16-byte aligned)
+    const uint32_t stage_s = smem_addr(smem);
+    const uint32_t ring_s = stage_s + (uint32_t)(2 * kFK * Cfg::kStagePitch);
+
+    if (warp < kFProd) {
+        // ==================================== producer warp: rows 2*warp, 2*warp + 1 of every step ====================
+        // copy plan of a row: chunk c = lane + 32 k holds image-row bytes [A0 + 16 c, +16); chunks outside the row are
+        // skipped (clamp-to-edge bytes are written by the fix-up below)
+        unsigned copy_mask = 0;
+#pragma unroll
+        for (int k = 0; k < Cfg::kCopyIters; k++) {
+            const int c = lane + 32 * k;
+            const int64_t g = A0 + 16 * (int64_t)c;
+            if (c < Cfg::kRowChunks && g >= 0 && g + 16 <= pitch) copy_mask |= 1u << k;
+        }
+        const int lane_dst = 16 * (lane + (lane >> 3));          // padded offset of chunk `lane`; chunk lane + 32 k is 576 k further
+        const int64_t lane_src = A0 + 16 * lane;
+        // clamp-to-edge: staged bytes left of image byte 0 (strip 0) and right of the last image byte
+        const int nleft = A0 < 0 ? (int)(-A0) : 0;               // staged indices [0, nleft)
+        const int64_t row_end_idx = pitch - A0;                  // staged index of the first byte past the row
+        const int nright = (row_end_idx < Cfg::kRowBytes) ? (int)((Cfg::kRowBytes - row_end_idx) < RC ? (Cfg::kRowBytes - row_end_idx) : RC) : 0;
+        const bool edge_strip = nleft > 0 || nright > 0;
+
+        const int64_t own_lo = job.src.band_y0 > 0 ? job.src.band_y0 : 0;
+        const int64_t own_hi = job.src.band_y1 < job.height ? job.src.band_y1 : job.height;
+        const int rel_fast_lo = (int)(own_lo + kFK - Ystart);    // row rel and row rel - K both lie in the band's own memory
+        const int rel_fast_hi = (int)(own_hi - Ystart);
+        const int64_t step_bytes = (int64_t)kFK * pitch;
+        const uint8_t* gsrc[2] = {nullptr, nullptr};
+        auto stage_rows = [&](int step) {                        // this warp's two rows of `step` into buffer step & 1
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int rel = step * kFK + 2 * warp + q;
+                if (rel < nrows_in) {
+                    if (rel >= rel_fast_lo && rel < rel_fast_hi && gsrc[q] != nullptr) gsrc[q] += step_bytes;
+                    else gsrc[q] = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img) + lane_src;
+                    const uint32_t dst = stage_s + (uint32_t)(((step & 1) * kFK + 2 * warp + q) * Cfg::kStagePitch + lane_dst);
+#pragma unroll
+                    for (int k = 0; k < Cfg::kCopyIters; k++)
+                        if ((copy_mask >> k) & 1) cp_async16(dst + 576 * k, gsrc[q] + 512 * k);
+                }
+            }
+            cp_async_commit();
+        };
+        // padded offsets of this lane's chunks: chunk 4*lane + i sits at lane_base + 16 i, plus 16 for i >= 4 in odd lanes
+        const int lane_base = 16 * (4 * lane + (lane >> 1));
+        const int lane_base_hi = lane_base + 16 * (lane & 1);
+
+        stage_rows(0);
+        stage_rows(1);
+        for (int step = 0; step <= nsteps; step++) {
+            if (step < nsteps) {
+                cp_async_wait<1>();                  // the rows of `step` have landed (the copies of step + 1 may be in flight)
+                __syncwarp();
+                const int rel = step * kFK + 2 * warp;
+                const uint32_t rowA = stage_s + (uint32_t)(((step & 1) * kFK + 2 * warp) * Cfg::kStagePitch);
+                const uint32_t rowB = rowA + Cfg::kStagePitch;
+                if (edge_strip && rel < nrows_in) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const uint32_t row = q ? rowB : rowA;
+                        for (int i = lane; i < nleft; i += 32) {         // image position A0 + i < 0 -> pixel 0, same channel
+                            const int ch = (int)(((A0 + i) % C + C) % C);
+                            uint32_t v;
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + padded_off(nleft + ch)));
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + padded_off(i)), "r"(v) : "memory");
+                        }
+                        for (int i = lane; i < nright; i += 32) {        // image position pitch + i -> last pixel, same channel
+                            const int src = (int)row_end_idx - C + (i % C), dst = (int)row_end_idx + i;
+                            uint32_t v;
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + padded_off(src)));
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + padded_off(dst)), "r"(v) : "memory");
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (rel < nrows_in) {
+                    // ---- H pass of rows rel (low halves of every pair) and rel + 1 (high halves)
+                    const uint32_t ringA = ring_s + (uint32_t)(((step & 1) * kFK + 2 * warp) * kFRingPitch + lane_base);
+                    const uint32_t ringB = ringA + kFRingPitch;
+                    uint32_t rawA[4 * Cfg::kLaneChunks], rawB[4 * Cfg::kLaneChunks];
+                    uint64_t f[kFLane + 2 * RC];                 // converted inputs (row A, row B); only 2RC+1 are live at a time
+                    uint32_t zA[4], zB[4], wA[4], wB[4];
+#pragma unroll
+                    for (int m = 0; m < kFLane + 2 * RC; m++) {
+                        const int bi = Cfg::kDelta + m;          // byte index inside the lane's chunks
+                        if (m == 0 || (bi & 15) == 0) {          // first byte of a chunk: load it for both rows
+                            const int i = bi >> 4;
+                            const uint32_t off = (uint32_t)((i < 4 ? lane_base : lane_base_hi) + 16 * i);
+                            const uint4 a = lds128(rowA + off), b = lds128(rowB + off);
+                            rawA[4 * i] = a.x; rawA[4 * i + 1] = a.y; rawA[4 * i + 2] = a.z; rawA[4 * i + 3] = a.w;
+                            rawB[4 * i] = b.x; rawB[4 * i + 1] = b.y; rawB[4 * i + 2] = b.z; rawB[4 * i + 3] = b.w;
+                        }
+                        f[m] = pack_f2(byte_to_float_bits(rawA[bi >> 2], bi & 3), byte_to_float_bits(rawB[bi >> 2], bi & 3));
+                        const int j = m - 2 * RC;                // the output byte this input completes
+                        if (j >= 0) {
+                            uint64_t acc = mul_rn_x2(f[j], splat_f2(job.weights[0]));
+#pragma unroll
+                            for (int t = 1; t < R2; t++) acc = fma_rn_x2(f[j + t * C], splat_f2(job.weights[t]), acc);
+                            const uint64_t z = round_pair_f(acc);
+                            zA[j & 3] = lo_f2(z); zB[j & 3] = hi_f2(z);
+                            if ((j & 3) == 3) {
+                                wA[(j >> 2) & 3] = __byte_perm(__byte_perm(zA[0], zA[1], 0x4040), __byte_perm(zA[2], zA[3], 0x4040), 0x5410);
+                                wB[(j >> 2) & 3] = __byte_perm(__byte_perm(zB[0], zB[1], 0x4040), __byte_perm(zB[2], zB[3], 0x4040), 0x5410);
+                            }
+                            if ((j & 15) == 15) {
+                                sts128(ringA + 16 * (j >> 4), wA[0], wA[1], wA[2], wA[3]);
+                                sts128(ringB + 16 * (j >> 4), wB[0], wB[1], wB[2], wB[3]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                        // every lane has read this buffer: refill it for step + 2
+                stage_rows(step + 2);
+            }
+            __syncthreads();
+        }
+    } else {
+        // ==================================== consumer warp ====================================
+        // Thread vt owns the 8-byte column group vt of the strip: 4 byte pairs, 2R+1 partial sums each.
+        const int vt = tid - 32 * kFProd;
+        const int64_t col = bxs + 8 * (int64_t)vt;
+        const bool any = col < pitch;                // pitch is a multiple of 16: a group is inside the row or outside it
+        const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vt >> 1) + (vt >> 4)) + 8 * (vt & 1));
+        uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;
+        uint64_t acc[4][R2];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int t = 0; t < R2; t++) acc[q][t] = 0;
+        for (int step = 0; step <= nsteps; step++) {
+            if (step >= 1 && any) {
+                const int s = step - 1;
+                const int rel0 = s * kFK;
+                const int nk = (nrows_in - rel0 < kFK) ? nrows_in - rel0 : kFK;
+                uint32_t a = ring_tid + (uint32_t)((s & 1) * kFK * kFRingPitch);
+#pragma unroll 2
+                for (int k = 0; k < nk; k++) {
+                    const uint2 w = lds64(a);
+                    a += kFRingPitch;
+                    const uint32_t ww[2] = {w.x, w.y};
+                    uint64_t v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        v[q] = pack_f2(byte_to_float_bits(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits(ww[q >> 1], 2 * (q & 1) + 1));
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+#pragma unroll
+                        for (int t = R2 - 1; t >= 1; t--) acc[q][t] = fma_rn_x2(v[q], splat_f2(job.weights[t]), acc[q][t - 1]);
+                        acc[q][0] = mul_rn_x2(v[q], splat_f2(job.weights[0]));
+                    }
+                    if (rel0 + k >= 2 * R) {         // the row that entered completes output row Y0 + rel - 2R
+                        uint32_t o[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const uint64_t z0 = round_pair_f(acc[2 * h][R2 - 1]), z1 = round_pair_f(acc[2 * h + 1][R2 - 1]);
+                            o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
+                        }
+                        stg64_stream(optr, o[0], o[1]);
+                        optr += pitch;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int R, int C>
+cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
+    using Cfg = FCfg<R, C>;
+    static bool attr_set[64] = {};           // per instantiation and per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_set[dev]) {
+        e = cudaFuncSetAttribute(gip_gauss_fused<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    const int sms = num_sms();
+    if (sms <= 0) return cudaErrorInvalidDevice;
+    FusedTiling tl;
+    const int64_t pitch = job.src.pitch;
+    tl.strips = (int)((pitch + kFStrip - 1) / kFStrip);
+    const int64_t rows = job.src.band_y1 - job.src.band_y0;
+    // Row bands: the band count with the smallest (waves of resident CTAs) x (row steps of a tile: its rows, the 2R
+    // rows that only fill the V accumulators, and the two-step pipeline fill).
+    const int64_t per_band = (int64_t)tl.strips * job.batch;
+    int64_t max_bands = rows / 16; if (max_bands < 1) max_bands = 1;
+    if (max_bands > 1024) max_bands = 1024;
+    int64_t want = 1, best_cost = -1;
+    for (int64_t nb = 1; nb <= max_bands; nb++) {
+        if (per_band * nb > 0x7fffffff) break;
+        const int64_t waves = (per_band * nb + sms - 1) / sms;
+        const int64_t cost = waves * ((rows + nb - 1) / nb + 2 * R + 2 * kFK);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; want = nb; }
+    }
+    tl.bands = (int)want;
+    tl.band_rows = (int)((rows + tl.bands - 1) / tl.bands);
+    const int64_t tiles = per_band * tl.bands;
+    if (tiles > 0x7fffffff) return cudaSuccess;          // two-kernel path
+    gip_gauss_fused<R, C><<<(unsigned)tiles, kFThreads, Cfg::kSmem, stream>>>(job, tl);
+    count_launch();
+    e = cudaGetLastError();
+    *handled = (e == cudaSuccess);
+    return e;
+}
+
+template <int R>
+cudaError_t run_fused_radius(const Job& job, cudaStream_t stream, bool* handled) {
+    if (job.channels == 4) return launch_fused<R, 4>(job, stream, handled);
+    if (job.channels == 3) return launch_fused<R, 3>(job, stream, handled);
+    return launch_fused<R, 1>(job, stream, handled);
+}
+
+}  // namespace
+}  // namespace gip
