@@ -26,6 +26,7 @@
 // The FP32 pipe is the roofline: 2 * ((2R+1) + 2) packed-lane operations per byte.
 #pragma once
 #include <cstring>
+#include <type_traits>
 #include "common.cuh"
 #include "device_utils.cuh"
 
@@ -37,7 +38,7 @@ constexpr int kFProd = 8, kFCons = 8;       // producer / consumer warps
 constexpr int kFThreads = 32 * (kFProd + kFCons);
 constexpr int kFStrip = 2048;               // output bytes per strip (32 lanes x 64 bytes)
 constexpr int kFLane = 64;
-constexpr int kFRingRows = 2 * kFK;
+constexpr int kFRingRows = 3 * kFK;         // the V pass consumes whole blocks of 2R+1 rows and may lag a step behind by up to 2R rows
 constexpr int kFRingPitch = kFStrip + kFStrip / 8;      // 2304: one pad chunk per 8 chunks
 
 // byte offset of byte `idx` of a row stored in the padded layout
@@ -178,7 +179,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 }
                 if (rel < nrows_in) {
                     // ---- H pass of rows rel (low halves of every pair) and rel + 1 (high halves)
-                    const uint32_t ringA = ring_s + (uint32_t)(((step & 1) * kFK + 2 * warp) * kFRingPitch + lane_base);
+                    const uint32_t ringA = ring_s + (uint32_t)(((step % 3) * kFK + 2 * warp) * kFRingPitch + lane_base);
                     const uint32_t ringB = ringA + kFRingPitch;
                     uint32_t rawA[4 * Cfg::kLaneChunks], rawB[4 * Cfg::kLaneChunks];
                     uint64_t f[kFLane + 2 * RC];                 // converted inputs (row A, row B); only 2RC+1 are live at a time
@@ -225,42 +226,54 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         const bool any = col < pitch;                // pitch is a multiple of 16: a group is inside the row or outside it
         const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vt >> 1) + (vt >> 4)) + 8 * (vt & 1));
         uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;
+        // Rows are consumed in blocks of 2R+1: inside a block the accumulator that takes tap k of row u is slot
+        // (u - k) mod (2R+1), a compile-time register, and after a block every slot is back where it started -- no register
+        // is ever moved.  Whole blocks only (the rows of a step that do not fill a block wait for the next step; the FIFO
+        // has three steps of rows for that), except at the end of the tile.
         uint64_t acc[4][R2];
 #pragma unroll
         for (int q = 0; q < 4; q++)
 #pragma unroll
             for (int t = 0; t < R2; t++) acc[q][t] = 0;
+        const uint32_t ring_end = ring_tid + (uint32_t)(kFRingRows * kFRingPitch);
+        uint32_t a = ring_tid;                       // FIFO row of input row `done`
+        int done = 0;                                // input rows consumed so far (a multiple of 2R+1)
+        auto v_block = [&](auto steady_tag) {
+            constexpr bool kSteady = decltype(steady_tag)::value;      // every row of the block emits an output row
+#pragma unroll
+            for (int u = 0; u < R2; u++) {
+                const uint2 w = lds64(a);
+                a += kFRingPitch; if (a == ring_end) a = ring_tid;
+                const uint32_t ww[2] = {w.x, w.y};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint64_t v = pack_f2(byte_to_float_bits(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits(ww[q >> 1], 2 * (q & 1) + 1));
+                    acc[q][u] = mul_rn_x2(v, splat_f2(job.weights[0]));
+#pragma unroll
+                    for (int k = 1; k < R2; k++)
+                        acc[q][(u - k + R2) % R2] = fma_rn_x2(v, splat_f2(job.weights[k]), acc[q][(u - k + R2) % R2]);
+                }
+                const int rel = done + u;
+                if (kSteady || (rel >= 2 * R && rel < nrows_in)) {     // this row completes output row Y0 + rel - 2R
+                    uint32_t o[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint64_t z0 = round_pair_f(acc[2 * h][(u + 1) % R2]), z1 = round_pair_f(acc[2 * h + 1][(u + 1) % R2]);
+                        o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
+                    }
+                    stg64_stream(optr, o[0], o[1]);
+                    optr += pitch;
+                }
+            }
+            done += R2;
+        };
         for (int step = 0; step <= nsteps; step++) {
-            if (step >= 1 && any) {
-                const int s = step - 1;
-                const int rel0 = s * kFK;
-                const int nk = (nrows_in - rel0 < kFK) ? nrows_in - rel0 : kFK;
-                uint32_t a = ring_tid + (uint32_t)((s & 1) * kFK * kFRingPitch);
-#pragma unroll 2
-                for (int k = 0; k < nk; k++) {
-                    const uint2 w = lds64(a);
-                    a += kFRingPitch;
-                    const uint32_t ww[2] = {w.x, w.y};
-                    uint64_t v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        v[q] = pack_f2(byte_to_float_bits(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits(ww[q >> 1], 2 * (q & 1) + 1));
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-#pragma unroll
-                        for (int t = R2 - 1; t >= 1; t--) acc[q][t] = fma_rn_x2(v[q], splat_f2(job.weights[t]), acc[q][t - 1]);
-                        acc[q][0] = mul_rn_x2(v[q], splat_f2(job.weights[0]));
-                    }
-                    if (rel0 + k >= 2 * R) {         // the row that entered completes output row Y0 + rel - 2R
-                        uint32_t o[2];
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const uint64_t z0 = round_pair_f(acc[2 * h][R2 - 1]), z1 = round_pair_f(acc[2 * h + 1][R2 - 1]);
-                            o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
-                        }
-                        stg64_stream(optr, o[0], o[1]);
-                        optr += pitch;
-                    }
+            if (any) {
+                const int avail = (step * kFK < nrows_in) ? step * kFK : nrows_in;      // rows of the steps before this one
+                const int target = (avail == nrows_in) ? nrows_in : avail - avail % R2;
+                while (done < target) {
+                    if (done >= 2 * R && done + R2 <= nrows_in) v_block(std::true_type{});
+                    else v_block(std::false_type{});
                 }
             }
             __syncthreads();
