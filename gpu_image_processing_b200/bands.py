@@ -169,7 +169,8 @@ class BandedImage:
     # -- filtering ----------------------------------------------------------------------------------
     def filter(self, kind: str, sigma: float = 2.0, radius: int = 3, level: int = 1,
                compute: Optional[Callable] = None) -> torch.Tensor:
-        """Rows [y0, y1) of filter(whole image).  Call exchange() first.  `compute(stitched, kind, params)` is a
+        """Rows [y0, y1) of filter(whole image).  Call exchange() first and finish() before `band` is rewritten (p2p
+        mode: neighbours read this rank's band while their kernels run).  `compute(stitched, kind, params)` is a
         test hook for CPU tensors (the product path has no CPU implementation)."""
         if halo_rows(kind, radius) > self.halo:
             raise ValueError("halo too small for this radius")
@@ -201,6 +202,15 @@ class BandedImage:
             raise ValueError(kind)
         _lib.check(rc)
         return self.out
+
+    def finish(self):
+        """Fence after filter() (p2p mode): filter() is stream-ordered and the neighbours' kernels read halo rows straight
+        out of this rank's `band` over NVLink, so `band` must not be rewritten (next frame) until every rank's filter()
+        has completed.  In a frame loop: write band -> exchange() -> filter() -> finish() -> write the next frame."""
+        if self.cuda:
+            torch.cuda.synchronize()
+        if self.mode == "p2p" and self.world > 1:
+            dist.barrier(group=self.group)
 
     def close(self):
         if self.mode == "p2p" and self.world > 1:

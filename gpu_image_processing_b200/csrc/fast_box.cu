@@ -40,6 +40,7 @@
 // constants (tools/box_magic.py, verified exhaustively in exact arithmetic) leaves
 // floor((S+r)/k) in the low mantissa byte of two sums at once: no integer divide, no I2F/F2I.
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <type_traits>
 #include "common.cuh"
@@ -456,7 +457,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
 
 template <int C, bool kVec, bool kDirect, int GB>
 cudaError_t launch(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, cudaStream_t stream) {
-    static bool attr_set[64] = {};   // per instantiation and per device: the opt-in is a per-device attribute
+    static std::atomic<bool> attr_set[64];   // per instantiation and per device: the opt-in is a per-device attribute
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

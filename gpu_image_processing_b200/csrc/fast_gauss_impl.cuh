@@ -21,6 +21,7 @@
 // The algorithm is FP32-issue bound, not HBM bound, from radius 3 up (4r+2 FMAs per byte); DESIGN.md
 // carries the instruction roofline next to the HBM one.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 #include "device_utils.cuh"
 
@@ -380,11 +381,15 @@ cudaError_t launch_h(const Job& job, uint8_t* tmp, int64_t tpitch, int64_t ty0, 
     const size_t smem = (size_t)kTileRows * (in_pitch + out_pitch);
     const int64_t blocks = (int64_t)tiles_x * tiles_y * nimg;
     if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
-    static bool set = false;
-    if (!set) {
+    static std::atomic<bool> attr_set[64];                        // per instantiation and per device: the opt-in is a per-device attribute
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(gip_gauss_h<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        set = true;
+        attr_set[dev].store(true, std::memory_order_release);
     }
     gip_gauss_h<R, C><<<(unsigned)blocks, HCfg<C, R>::kThreads, smem, stream>>>(job, tmp, ty0, ty1, img0, tiles_x, tiles_y,
                                                                              in_pitch, out_pitch, tpitch);
@@ -400,7 +405,12 @@ cudaError_t launch_v(const Job& job, const uint8_t* tmp, int64_t tpitch, int64_t
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     const bool aligned_out = (job.src.pitch % 4 == 0) && (job.src.image_stride % 4 == 0) && ((uintptr_t)job.out % 4 == 0);
     const int64_t col_blocks = aligned_out ? (words + 127) / 128 : (words + 123) / 124;   // unaligned: 4 warps x 31 columns
-    static int per_sm[2] = {0, 0};                                // resident blocks per SM of the two variants
+    static std::atomic<int> per_sm_cache[64][2];                  // resident blocks per SM of the two variants, per device
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::atomic<int>* per_sm = per_sm_cache[dev];
     if (per_sm[aligned_out] == 0) {
         int n = 0;
         cudaError_t e = aligned_out ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gip_gauss_v<R, true>, 128, 0)

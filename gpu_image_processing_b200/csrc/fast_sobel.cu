@@ -24,6 +24,7 @@
 // The edge value is replicated into every channel, alpha included (:1311-1313).
 // Warps whose 32 lanes all lie inside the row (every strip but the first and the last one or two of a
 // row) run a path without per-word offsets, masks and store predicates.
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
@@ -379,7 +380,7 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
 template <int C, bool kU8, int VB>
 cudaError_t launch(const Job& job, SobelTiling tl, int64_t per_band, int64_t rows, cudaStream_t stream, bool* handled) {
     // Resident warps per SM of this instantiation on the current device (the attribute is per device).
-    static int per_sm_cache[64] = {};
+    static std::atomic<int> per_sm_cache[64];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

@@ -25,6 +25,7 @@
 // tap in tap order, (uchar)(sum + 0.5f) == low mantissa byte of RZ(RN(sum + 0.5f) + 2^23).
 // The FP32 pipe is the roofline: 2 * ((2R+1) + 2) packed-lane operations per byte.
 #pragma once
+#include <atomic>
 #include <cstring>
 #include <type_traits>
 #include "common.cuh"
@@ -284,7 +285,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
 template <int R, int C>
 cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
     using Cfg = FCfg<R, C>;
-    static bool attr_set[64] = {};           // per instantiation and per device
+    static std::atomic<bool> attr_set[64];           // per instantiation and per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

@@ -400,3 +400,65 @@ def test_bands_with_exactly_the_promised_halo_rows(c, path):
         got = np.concatenate([t.cpu().numpy() for t in outs], axis=0)
         want = {"sobel": lambda: O.sobel(img, 2), "box": lambda: O.box_blur(img, 1), "gaussian": lambda: O.gaussian_blur(img, 1.0, 1)}[kind]()
         _check(kind, got, want, kind + " one-row bands")
+
+
+def test_c2_box_radius_sweep_as_benched():
+    """BASELINE config c2 exactly as bench.py times it: box blur r = 1..31 on a 4096 x 4096 RGBA image, every radius
+    against the oracle on row bands (top edge, an interior band, bottom edge)."""
+    import torch
+    from gpu_image_processing_b200 import device
+    h = w = 4096
+    c = 4
+    img = synth.uniform(h, w, c, seed=2024)
+    x = torch.from_numpy(img).cuda()
+    y = torch.empty_like(x)
+    n = 24
+    for r in range(1, 32):
+        device.box_blur(x, r, 2, out=y)
+        out = y.cpu().numpy()
+        _check("box", out[:n], O.box_blur(img[:n + r], r)[:n], f"c2 r={r} top rows")
+        _check("box", out[-n:], O.box_blur(img[-(n + r):], r)[-n:], f"c2 r={r} bottom rows")
+        _interior_band_check("box", img, out, h // 2 - 8 + r, h // 2 + 8 + r, r)
+
+
+def test_first_call_time_ms_excludes_the_module_load():
+    """The reference's time_ms is kernel time (image_filters.cu:804, :893-901): the first call that reaches a kernel
+    variant must not report CUDA's lazy module load (tens of ms) as filter time.  Run in a fresh process."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, gpu_filters\n"
+            "img = np.random.default_rng(1).integers(0, 256, (270, 480, 3), dtype=np.uint8)\n"
+            "t = [gpu_filters.gaussian_blur(img, 2.0, 3, 1)['time_ms'], gpu_filters.box_blur(img, 3, 1)['time_ms'],\n"
+            "     gpu_filters.sobel_edge_detection(img, 1)['time_ms']]\n"
+            "print(max(t))\n")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert float(out.stdout.strip().splitlines()[-1]) < 2.0, out.stdout      # ms; a 389 KB image takes a few us
+
+
+def test_two_devices_in_one_process():
+    """include/image_filters.h: "the current device is whatever the caller set".  Shared-memory opt-ins, occupancy and
+    SM counts are per-device state: every filter on cuda:0, then on cuda:1, in this one process (box r = 31 on RGBA
+    needs > 48 KB of dynamic shared memory, Gaussian r = 9 takes the two-kernel path, r = 3 the fused one)."""
+    import torch
+    from gpu_image_processing_b200 import device
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    img4 = synth.uniform(200, 1024, 4, seed=3)
+    img3 = synth.uniform(200, 1024, 3, seed=4)
+    want = [("box", O.box_blur(img4, 31)), ("box", O.box_blur(img3, 3)), ("gaussian", O.gaussian_blur(img3, 2.0, 3)),
+            ("gaussian", O.gaussian_blur(img3, 3.0, 9)), ("gaussian", O.gaussian_blur(img3, 8.0, 24)),
+            ("sobel", O.sobel(img3, 1)), ("sobel", O.sobel(img4, 2))]
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            x4 = torch.from_numpy(img4).to(f"cuda:{dev}")
+            x3 = torch.from_numpy(img3).to(f"cuda:{dev}")
+            got = [device.box_blur(x4, 31, 2), device.box_blur(x3, 3, 1), device.gaussian_blur(x3, 2.0, 3, 1),
+                   device.gaussian_blur(x3, 3.0, 9, 2), device.gaussian_blur(x3, 8.0, 24, 2),
+                   device.sobel_edge_detection(x3, 1), device.sobel_edge_detection(x4, 2)]
+            torch.cuda.synchronize(dev)
+            for (kind, w_), g_ in zip(want, got):
+                assert g_.device.index == dev
+                _check(kind, g_.cpu().numpy(), w_, f"{kind} on cuda:{dev}")
