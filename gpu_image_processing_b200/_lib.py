@@ -34,6 +34,8 @@ SIGNATURES = {
     "gip_gaussian_blur_host": (i32, [u8p, u8p, i64, i64, i32, i64, f32, i32, i32, mp]),
     "gip_box_blur_host": (i32, [u8p, u8p, i64, i64, i32, i64, i32, i32, mp]),
     "gip_sobel_host": (i32, [u8p, u8p, i64, i64, i32, i64, i32, mp]),
+    "gip_host_alloc": (i32, [i64, ctypes.POINTER(ctypes.c_void_p)]),
+    "gip_host_free": (i32, [ctypes.c_void_p]),
     "gip_device_alloc": (i32, [i64, ctypes.POINTER(ctypes.c_void_p)]),
     "gip_device_free": (i32, [ctypes.c_void_p]),
     "gip_ipc_export": (i32, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -312,8 +312,13 @@ static size_t host_chunk_bytes() {
     return v;
 }
 static int host_threads() {
-    static const int v = (int)env_long("GIP_HOST_THREADS", 4);
-    return v < 2 ? 2 : (v > 16 ? 16 : v);
+    static const int v = [] {
+        const unsigned hw = std::thread::hardware_concurrency();
+        long dflt = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);           // a memcpy thread moves ~8 GB/s; PCIe Gen5 x16 wants ~50
+        long t = env_long("GIP_HOST_THREADS", dflt);
+        return (int)(t < 2 ? 2 : (t > 16 ? 16 : t));
+    }();
+    return v;
 }
 
 static bool is_pinned(const void* p) {
@@ -459,7 +464,9 @@ static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out
     } else {
         HostProgress prog;
         const int dev = c.device;
-        const int t_in = pin_in ? 0 : host_threads() / 2, t_out = pin_out ? 0 : host_threads() - host_threads() / 2;
+        // staging threads: split between the two directions, or all on the one direction that needs them
+        const int t_in = pin_in ? 0 : (pin_out ? host_threads() : host_threads() / 2);
+        const int t_out = pin_out ? 0 : (pin_in ? host_threads() : host_threads() - host_threads() / 2);
         std::vector<std::thread> workers;
         for (int j = 0; j < t_in; j++)
             workers.emplace_back([&, j] {                          // stage slice j of every chunk; last one in uploads
@@ -633,6 +640,12 @@ int gip_enable_peer_access(int peer_device) {
     if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); err = cudaSuccess; }
     return (int)err;
 }
+
+int gip_host_alloc(int64_t bytes, void** h_ptr_out) {
+    if (bytes <= 0 || !h_ptr_out) return (int)cudaErrorInvalidValue;
+    return (int)cudaHostAlloc(h_ptr_out, (size_t)bytes, cudaHostAllocPortable);
+}
+int gip_host_free(void* h_ptr) { return (int)cudaFreeHost(h_ptr); }
 
 int gip_gaussian_weights(float* weights_out, int radius, float sigma) {
     if (!weights_out || radius < 0 || !(sigma > 0.0f)) return (int)cudaErrorInvalidValue;

@@ -12,7 +12,8 @@ py::array_t<unsigned char> does.  Returns {"image": uint8 (H,W,C), "time_ms", "b
 
 Differences: the array is made C-contiguous first (the reference reads a strided buffer as if
 it were dense); device and pinned buffers are cached between calls instead of cudaMalloc/cudaFree
-per call (bindings.cpp:37-39, :80-81); the GIL is released while the GPU works (ctypes).
+per call (bindings.cpp:37-39, :80-81); the result array lives in pooled page-locked memory (the download
+lands in it directly); the GIL is released while the GPU works (ctypes).
 """
 from __future__ import annotations
 
@@ -27,6 +28,57 @@ SHARED_MEMORY = 2
 TEXTURE_MEMORY = 3
 
 
+class _ResultPool:
+    """Result arrays in page-locked memory.  The reference returns a fresh pageable array (bindings.cpp:77-81), which costs
+    a staging copy and a page fault per 4 KB on every call; here the download lands directly in the array the caller
+    gets.  A block goes back to the pool when the array (and every view of it) has been garbage-collected.  Bounded: at most
+    GIP_RESULT_POOL_MB (default 2048) of pinned memory is held (cached + handed out); beyond that, or for arrays
+    below 256 KB, results are ordinary pageable arrays."""
+
+    MIN_BYTES = 256 << 10
+
+    def __init__(self):
+        import os
+        import threading
+        self.cap = int(os.environ.get("GIP_RESULT_POOL_MB", "2048")) << 20
+        self.free = {}            # nbytes -> [ptr, ...]
+        self.held = 0             # bytes allocated from the driver (free lists + handed out)
+        self.lock = threading.Lock()
+
+    def _release(self, ptr, nbytes):
+        with self.lock:
+            self.free.setdefault(nbytes, []).append(ptr)
+
+    def empty(self, shape):
+        import weakref
+        nbytes = int(np.prod(shape))
+        if nbytes < self.MIN_BYTES or self.cap <= 0:
+            return np.empty(shape, dtype=np.uint8)
+        with self.lock:
+            lst = self.free.get(nbytes)
+            ptr = lst.pop() if lst else None
+            if ptr is None and self.held + nbytes > self.cap:      # make room: drop cached blocks of other sizes
+                for size in list(self.free):
+                    while self.free[size] and self.held + nbytes > self.cap:
+                        _lib.load().gip_host_free(self.free[size].pop())
+                        self.held -= size
+                if self.held + nbytes > self.cap:
+                    return np.empty(shape, dtype=np.uint8)
+            if ptr is None:
+                p = ctypes.c_void_p()
+                if _lib.load().gip_host_alloc(nbytes, ctypes.byref(p)) != 0 or not p.value:
+                    return np.empty(shape, dtype=np.uint8)
+                ptr = p.value
+                self.held += nbytes
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.uint8).reshape(shape)
+        weakref.finalize(buf, self._release, ptr, nbytes)          # buf lives as long as arr or any view of it
+        return arr
+
+
+_pool = _ResultPool()
+
+
 def _prepare(image):
     a = np.asarray(image)
     if a.ndim != 3:
@@ -39,7 +91,7 @@ def _prepare(image):
         raise RuntimeError("Channels must be 1, 3, or 4")
     if h == 0 or w == 0:
         raise RuntimeError("CUDA error: invalid argument")
-    return a, np.empty_like(a), h, w, c
+    return a, _pool.empty(a.shape), h, w, c
 
 
 def _result(out, m):

@@ -109,6 +109,13 @@ int gip_box_blur_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, 
 int gip_sobel_host(const uint8_t* h_input, uint8_t* h_output, int64_t width, int64_t height,
                    int channels, int64_t batch, int level, gip_metrics* metrics);
 
+/* ---- pinned host memory -------------------------------------------------------------------------
+ * The host entry points above run at PCIe speed when the caller's buffers are page-locked (no staging copy).
+ * gip_host_alloc returns such memory (cudaHostAlloc, portable); the `gpu_filters` module hands out result arrays
+ * from a pool of these.  Replaces the pageable numpy result of bindings.cpp:77-81. */
+int gip_host_alloc(int64_t bytes, void** h_ptr_out);
+int gip_host_free(void* h_ptr);
+
 /* ---- peer memory for row bands across processes (CUDA IPC) --------------------------------
  * gip_device_alloc returns plain cudaMalloc memory (framework caching allocators sub-allocate, and CUDA IPC
  * exports whole allocations).  gip_ipc_export writes a 64-byte handle for such a base pointer; another process on

@@ -462,3 +462,40 @@ def test_two_devices_in_one_process():
             for (kind, w_), g_ in zip(want, got):
                 assert g_.device.index == dev
                 _check(kind, g_.cpu().numpy(), w_, f"{kind} on cuda:{dev}")
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+@pytest.mark.parametrize("r,sigma", [(16, 5.0), (19, 6.5), (24, 8.0), (27, 3.0), (31, 10.0)])
+def test_gaussian_wide_radii_fast_path(c, r, sigma):
+    """Radii 16..31 (the reference's level 2 accepts 2r+1 <= 64 taps, image_filters.cu:729) on the shift-formulation
+    kernels: whole images of awkward sizes (narrower / shorter than the window, odd pitches), a batch, and row bands."""
+    import torch
+    from gpu_image_processing_b200 import device
+    L = _lib.load()
+    before = L.gip_launch_count()
+    for h, w in ((1, 1), (3, 200), (200, 3), (45, 61), (130, 517), (300, 1025)):
+        img = synth.uniform(h, w, c, seed=h * 7 + w + r)
+        out = gpu_filters.gaussian_blur(img, sigma=sigma, radius=r, level=2)["image"]
+        _check("gaussian", out, O.gaussian_blur(img, sigma, r), f"wide gaussian {h}x{w} c={c} r={r}")
+    frames = np.stack([synth.smooth(150, 333, c, seed=s) for s in range(3)])
+    got = device.gaussian_blur(torch.from_numpy(frames).cuda(), sigma, r, 1).cpu().numpy()
+    for i in range(3):
+        _check("gaussian", got[i], O.gaussian_blur(frames[i], sigma, r), f"wide gaussian batch c={c} r={r}")
+    # row bands with halo pointers
+    h, w = 260, 301
+    img = synth.uniform(h, w, c, seed=r)
+    x = torch.from_numpy(img).cuda()
+    out = torch.zeros_like(x)
+    pitch = w * c
+    cuts = [0, 70, 131, 200, 260]
+    stream = torch.cuda.current_stream().cuda_stream
+    for y0, y1 in zip(cuts[:-1], cuts[1:]):
+        ra, rb = min(r, y0), min(r, h - y1)
+        rc = L.gip_gaussian_blur_band(x.data_ptr() + y0 * pitch, x.data_ptr() + (y0 - ra) * pitch if ra else None,
+                                      x.data_ptr() + y1 * pitch if rb else None, out.data_ptr() + y0 * pitch, w, h, c,
+                                      y0, y1 - y0, ra, rb, sigma, r, 1, stream)
+        assert rc == 0
+    torch.cuda.synchronize()
+    _check("gaussian", out.cpu().numpy(), O.gaussian_blur(img, sigma, r), f"wide gaussian bands c={c} r={r}")
+    # two launches (H, V) per call on the fast path; the general path would also be two, so check the kernel is the fast one
+    assert L.gip_launch_count() - before >= 2 * (6 + 1 + 4)

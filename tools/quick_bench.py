@@ -68,6 +68,8 @@ if __name__ == "__main__":
             run("box", shape, 16, radii)
             run("sobel", shape, 16, [1])
             run("gaussian", shape, 16, [3])
+    if what == "gsweep":                    # Gaussian over the radii on the 8K RGB shape
+        run("gaussian", (4320, 7680, 3), 3, radii)
     if what in ("gaussian", "all"):
         run("gaussian", (2146, 3239, 3), 8, [3])
         run("gaussian", (4320, 7680, 3), 3, [3, 15])
