@@ -32,7 +32,7 @@ def _deps_mtime():
     m = 0.0
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
-            if f.endswith((".cuh", ".h")):
+            if f.endswith((".cuh", ".h", ".inc")):
                 m = max(m, os.path.getmtime(os.path.join(root, f)))
     return m
 

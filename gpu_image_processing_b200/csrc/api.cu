@@ -63,20 +63,41 @@ struct BandArgs {
     int64_t y0 = 0, rows = -1, rows_above = 0, rows_below = 0;
 };
 
-// Stream-ordered scratch (cudaMallocAsync) must not go back to the OS at every synchronisation:
-// keep the default pool's memory cached (set once per device).
-static void keep_pool_cached() {
-    static std::atomic<unsigned long long> done_mask{0};
+// Stream-ordered scratch.  The general and two-kernel Gaussian paths allocate up to 1 GiB per call; giving that back to
+// the driver at every synchronisation (the default release threshold is 0) costs milliseconds per call, so the scratch
+// comes from a pool owned by this library, one per device, whose release threshold is unlimited: it retains its
+// high-water mark until gip_release_cache() trims it (documented in gip_b200.h).
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
+
+static cudaError_t scratch_pool(cudaMemPool_t* out) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-    const unsigned long long bit = 1ull << dev;
-    if (done_mask.load() & bit) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if ((err = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return err;
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        g_pools[dev] = pool;
     }
-    done_mask.fetch_or(bit);
+    *out = g_pools[dev];
+    return cudaSuccess;
+}
+
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t stream) {
+    cudaMemPool_t pool = nullptr;
+    cudaError_t err = scratch_pool(&pool);
+    if (err != cudaSuccess) return err;
+    return cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
 }
 
 // Validate and enqueue one filter.  All entry points funnel through here.
@@ -92,7 +113,6 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
     if (kind != kSobel && radius < 0) return cudaErrorInvalidValue;
     if (kind == kGaussian && !(sigma > 0.0f)) return cudaErrorInvalidValue;
     if (kind == kSobel) radius = 1;
-    keep_pool_cached();
 
     Job job;
     memset(&job, 0, sizeof(job));
@@ -127,7 +147,7 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
         const size_t out_bytes = (size_t)job.src.pitch * (size_t)(job.src.band_y1 - job.src.band_y0) * (size_t)batch;
         const uintptr_t i0 = (uintptr_t)d_in, o0 = (uintptr_t)d_out;
         if (i0 < o0 + out_bytes && o0 < i0 + out_bytes) {
-            if ((err = cudaMallocAsync((void**)&d_copy, out_bytes, stream)) != cudaSuccess) return err;
+            if ((err = scratch_alloc((void**)&d_copy, out_bytes, stream)) != cudaSuccess) return err;
             if ((err = cudaMemcpyAsync(d_copy, d_in, out_bytes, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) {
                 cudaFreeAsync(d_copy, stream);
                 return err;
@@ -151,7 +171,7 @@ static cudaError_t enqueue(FilterKind kind, const uint8_t* d_in, uint8_t* d_out,
             float* h = (float*)malloc(n * sizeof(float));
             if (!h) { if (d_copy) cudaFreeAsync(d_copy, stream); return cudaErrorMemoryAllocation; }
             gaussian_weights_host(h, radius, sigma);
-            err = cudaMallocAsync((void**)&d_wide, n * sizeof(float), stream);
+            err = scratch_alloc((void**)&d_wide, n * sizeof(float), stream);
             if (err == cudaSuccess)   // pageable source: staged before the call returns
                 err = cudaMemcpyAsync(d_wide, h, n * sizeof(float), cudaMemcpyHostToDevice, stream);
             free(h);
@@ -657,11 +677,13 @@ int64_t gip_launch_count(void) { return g_launches.load(); }
 int gip_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_cache.mu);
     g_cache.release();
-    int dev = 0;                                   // also hand the stream-ordered scratch pool back to the driver
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        cudaDeviceSynchronize();
-        cudaMemPoolTrimTo(pool, 0);
+    int dev = 0;                                   // also hand the library's scratch pool of this device back to the driver
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> plock(g_pool_mu);
+        if (g_pools[dev]) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(g_pools[dev], 0);
+        }
     }
     cudaGetLastError();
     return 0;

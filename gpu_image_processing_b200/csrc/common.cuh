@@ -49,6 +49,10 @@ cudaError_t launch_general(FilterKind kind, const Job& job, const float* d_wide_
 cudaError_t launch_fast(FilterKind kind, const Job& job, cudaStream_t stream, bool* handled);
 
 void count_launch(int n = 1);
+// Stream-ordered scratch from the library's own memory pool of the current device (freed with cudaFreeAsync).  The pool
+// keeps what it has been given until gip_release_cache(); the device's default pool -- shared with any other
+// cudaMallocAsync user in the process -- is left alone.
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t stream);
 int num_sms();   // SM count of the current device (cached per device)
 
 __host__ __device__ __forceinline__ int64_t clamp64(int64_t v, int64_t lo, int64_t hi) {

@@ -565,12 +565,13 @@ gip_gauss_wv(const __grid_constant__ Job job, const uint8_t* __restrict__ tmp, i
         issue(s + P);
     };
     auto emit = [&]() {
-        uint32_t o = 0;
+        uint32_t t[NP];
 #pragma unroll
         for (int q = 0; q < NP; q++) {
             const uint64_t z = round_pair(acc[q][2 * R]);
-            o |= __byte_perm(lo_f2(z), hi_f2(z), 0x4040) << (16 * q);
+            t[q] = __byte_perm(lo_f2(z), hi_f2(z), 0x4040);       // the pair's two bytes in the low half
         }
+        const uint32_t o = (NP == 2) ? __byte_perm(t[0], t[NP - 1], 0x5410) : t[0];
         if (out_aligned) {
             if (NP == 2) stg32_stream(optr, o);
             else *reinterpret_cast<unsigned short*>(optr) = (unsigned short)o;
@@ -696,7 +697,7 @@ cudaError_t run_radius(const Job& job, cudaStream_t stream) {
     if (chunk > job.batch) chunk = job.batch;
     if (chunk > 2048) chunk = 2048;
     uint8_t* tmp = nullptr;
-    cudaError_t err = cudaMallocAsync((void**)&tmp, (size_t)(chunk * trows * tpitch), stream);
+    cudaError_t err = scratch_alloc((void**)&tmp, (size_t)(chunk * trows * tpitch), stream);
     if (err != cudaSuccess) return err;
     for (int64_t img0 = 0; img0 < job.batch && err == cudaSuccess; img0 += chunk) {
         const int64_t n = (job.batch - img0 < chunk) ? job.batch - img0 : chunk;

@@ -1,6 +1,6 @@
 // fast_gauss_r01.cu -- radius 1 instantiation of the two-kernel Gaussian (one translation unit per radius so that
-// they compile in parallel; see fast_gauss_impl.cuh).  rotate = rotating accumulators, unrolled 2R+1 times (radius <= 15);
-// shift = partial sums move through the FMA destination, rolled loops (radius >= 5).
+// they compile in parallel; see fast_gauss_impl.cuh).  Radius <= 15: rotating accumulators, unrolled 2R+1 times.
+// Radius >= 16: shift formulation, rolled loops.
 #include "fast_gauss_impl.cuh"
 
 namespace gip {

@@ -1,9 +1,8 @@
 // fast_gauss_r09.cu -- radius 9 instantiation of the two-kernel Gaussian (one translation unit per radius so that
-// they compile in parallel; see fast_gauss_impl.cuh).  rotate = rotating accumulators, unrolled 2R+1 times (radius <= 15);
-// shift = partial sums move through the FMA destination, rolled loops (radius >= 5).
+// they compile in parallel; see fast_gauss_impl.cuh).  Radius <= 15: rotating accumulators, unrolled 2R+1 times.
+// Radius >= 16: shift formulation, rolled loops.
 #include "fast_gauss_impl.cuh"
 
 namespace gip {
 cudaError_t gauss_run_r09(const Job& job, cudaStream_t stream) { return run_radius<9, false>(job, stream); }
-cudaError_t gauss_shift_r09(const Job& job, cudaStream_t stream) { return run_radius<9, true>(job, stream); }
 }  // namespace gip

@@ -155,7 +155,7 @@ cudaError_t launch_general(FilterKind kind, const Job& job, const float* d_wide,
     if (chunk < 1) chunk = 1;
     if (chunk > job.batch) chunk = job.batch;
     uint8_t* tmp = nullptr;
-    cudaError_t err = cudaMallocAsync((void**)&tmp, (size_t)(chunk * trows * pitch), stream);
+    cudaError_t err = scratch_alloc((void**)&tmp, (size_t)(chunk * trows * pitch), stream);
     if (err != cudaSuccess) return err;
     const unsigned gx = (unsigned)((pitch + kThreads - 1) / kThreads);
     for (int64_t img0 = 0; img0 < job.batch && err == cudaSuccess; img0 += chunk) {

@@ -31,23 +31,27 @@ TEXTURE_MEMORY = 3
 class _ResultPool:
     """Result arrays in page-locked memory.  The reference returns a fresh pageable array (bindings.cpp:77-81), which costs
     a staging copy and a page fault per 4 KB on every call; here the download lands directly in the array the caller
-    gets.  A block goes back to the pool when the array (and every view of it) has been garbage-collected.  Bounded: at most
-    GIP_RESULT_POOL_MB (default 2048) of pinned memory is held (cached + handed out); beyond that, or for arrays
-    below 256 KB, results are ordinary pageable arrays."""
+    gets.  A block goes back to the pool when the array (and every view of it) has been garbage-collected.
+    Page-locking is expensive (~1 ms per MB), so the pool only pays it for callers that drop their results: at most
+    MAX_LIVE blocks of one size are handed out at a time and at most GIP_RESULT_POOL_MB (default 2048) of pinned memory
+    is held; a caller that hoards results, and arrays below 256 KB, get ordinary pageable arrays."""
 
     MIN_BYTES = 256 << 10
+    MAX_LIVE = 4
 
     def __init__(self):
         import os
         import threading
         self.cap = int(os.environ.get("GIP_RESULT_POOL_MB", "2048")) << 20
         self.free = {}            # nbytes -> [ptr, ...]
+        self.live = {}            # nbytes -> blocks handed out and not yet collected
         self.held = 0             # bytes allocated from the driver (free lists + handed out)
         self.lock = threading.Lock()
 
     def _release(self, ptr, nbytes):
         with self.lock:
             self.free.setdefault(nbytes, []).append(ptr)
+            self.live[nbytes] -= 1
 
     def empty(self, shape):
         import weakref
@@ -55,6 +59,8 @@ class _ResultPool:
         if nbytes < self.MIN_BYTES or self.cap <= 0:
             return np.empty(shape, dtype=np.uint8)
         with self.lock:
+            if self.live.get(nbytes, 0) >= self.MAX_LIVE:
+                return np.empty(shape, dtype=np.uint8)
             lst = self.free.get(nbytes)
             ptr = lst.pop() if lst else None
             if ptr is None and self.held + nbytes > self.cap:      # make room: drop cached blocks of other sizes
@@ -70,6 +76,7 @@ class _ResultPool:
                     return np.empty(shape, dtype=np.uint8)
                 ptr = p.value
                 self.held += nbytes
+            self.live[nbytes] = self.live.get(nbytes, 0) + 1
         buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
         arr = np.frombuffer(buf, dtype=np.uint8).reshape(shape)
         weakref.finalize(buf, self._release, ptr, nbytes)          # buf lives as long as arr or any view of it

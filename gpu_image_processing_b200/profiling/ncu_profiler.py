@@ -66,8 +66,14 @@ def _child_script(filter_type: str, level: int, sigma, radius) -> str:
             "print('profiled', r['time_ms'])\n")
 
 
-def parse_ncu_raw_csv(text: str) -> Dict[str, Any]:
-    """`ncu --page raw --csv` -> the reference's categorised dict.  One CSV row per kernel launch."""
+PROFILED_CALLS = 3      # filter calls made by the profiled child (_child_script)
+
+
+def parse_ncu_raw_csv(text: str, calls: int = 1) -> Dict[str, Any]:
+    """`ncu --page raw --csv` -> the reference's categorised dict.  One CSV row per kernel launch; `calls` = filter calls
+    the launches belong to.  A call is NOT one launch per kernel: the host path cuts images of 8 MB and more into up to
+    32 row-band chunks with one band launch each, so durations and DRAM bytes are summed over all launches and divided
+    by the number of calls."""
     metrics: Dict[str, Any] = {"occupancy": {}, "memory": {}, "warp": {}, "execution": {}, "throughput": {},
                                "config": {}, "kernel_durations": {}}
     rows = list(csv.reader(io.StringIO(text[text.find('"ID"'):] if '"ID"' in text else text)))
@@ -105,8 +111,9 @@ def parse_ncu_raw_csv(text: str) -> Dict[str, Any]:
         metrics["config"]["block_size"] = last[col["launch__block_size"]]
     if "launch__grid_size" in col:
         metrics["config"]["grid_size"] = last[col["launch__grid_size"]]
-    # one filter call = one launch of every kernel in `per_kernel`: average the launches of each kernel
-    metrics["kernel_durations"] = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+    calls = max(1, int(calls))
+    metrics["kernel_durations"] = {k: sum(v) / calls for k, v in per_kernel.items()}       # ms per filter call
+    metrics["launches_per_call"] = {k: len(v) / calls for k, v in per_kernel.items()}
     metrics["total_kernel_duration_ms"] = sum(metrics["kernel_durations"].values())
     metrics["kernels_profiled"] = list(metrics["kernel_durations"].keys())
     metrics["total_kernels"] = len(metrics["kernel_durations"])
@@ -114,9 +121,9 @@ def parse_ncu_raw_csv(text: str) -> Dict[str, Any]:
     if rd is not None and wr is not None and metrics["total_kernel_duration_ms"] > 0:
         def to_bytes(i):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
-            return sum(float(r[i].replace(",", "")) for r in launches if len(r) == len(header)) * scale / max(1, len(launches))
-        per_launch = to_bytes(rd) + to_bytes(wr)
-        metrics["memory"]["dram_bytes_per_launch"] = per_launch
+            return sum(float(r[i].replace(",", "")) for r in launches if len(r) == len(header)) * scale / calls
+        metrics["memory"]["dram_bytes_per_call"] = to_bytes(rd) + to_bytes(wr)
+        metrics["memory"]["dram_bytes_per_launch"] = metrics["memory"]["dram_bytes_per_call"]     # (key kept for the UI table)
     return metrics
 
 
@@ -137,7 +144,7 @@ def profile_kernel_with_ncu(img_array: np.ndarray, filter_type: str, level: int,
         rep = os.path.join(tmpdir, "profile")
         env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
         cmd = ["ncu", "--set", "full", "--clock-control", "none", "--kernel-name", KERNEL_PATTERNS[filter_type],
-               "--launch-skip", "0", "--launch-count", "10", "--export", rep, "--force-overwrite", sys.executable, script, npy]
+               "--launch-skip", "0", "--launch-count", "400", "--export", rep, "--force-overwrite", sys.executable, script, npy]
         run = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         if run.returncode != 0 or not os.path.exists(rep + ".ncu-rep"):
             raise RuntimeError(f"ncu failed (rc={run.returncode}): {(run.stderr or run.stdout)[-400:]}")
@@ -145,7 +152,7 @@ def profile_kernel_with_ncu(img_array: np.ndarray, filter_type: str, level: int,
                               text=True, timeout=300)
         if page.returncode != 0:
             raise RuntimeError(f"ncu --import failed: {page.stderr[-400:]}")
-        metrics = parse_ncu_raw_csv(page.stdout)
+        metrics = parse_ncu_raw_csv(page.stdout, calls=PROFILED_CALLS)
         metrics["filter"], metrics["level"] = filter_type, int(level)
         return metrics
     finally:
@@ -185,5 +192,5 @@ def get_common_ncu_metrics(metrics: Dict[str, Any], ncu_data: Optional[Dict] = N
             common["kernels_profiled"] = src["kernels_profiled"]
             common["total_kernels"] = len(src["kernels_profiled"])
         if common.get("dram_bytes_per_launch") and common["time_ms"] > 0:
-            common["achieved_dram_gbps"] = common["dram_bytes_per_launch"] * max(1, common.get("total_kernels", 1)) / (common["time_ms"] / 1e3) / 1e9
+            common["achieved_dram_gbps"] = common["dram_bytes_per_launch"] / (common["time_ms"] / 1e3) / 1e9
     return common

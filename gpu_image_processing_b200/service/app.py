@@ -5,7 +5,9 @@ Same routes, request/response models, status codes and texts:
     POST /api/process      app.py:186-284      body {image, filter, level=1, sigma=2.0, radius=3, enable_profiling=false}
                                                -> {processed_image: "data:image/png;base64,...", metrics{time_ms,bandwidth_gbps,fps}, info{...}}
                                                503 module missing, 400 bad filter / level, 500 everything else
-    POST /api/process-all  app.py:286-470      both levels + optional ncu metrics, keys level_1 / level_2
+    POST /api/process-all  app.py:286-494      both levels + optional ncu metrics, keys level_1 / level_2; a level that fails is
+                                               logged and skipped, 500 only when no level succeeded (app.py:461-475)
+    POST /api/upload       app.py:496-524      multipart file -> {base64_image, width, height, channels}
 Images are decoded with PIL and forced to RGB like the reference (app.py:80-83).  Handlers are plain `def`:
 FastAPI runs them in its thread pool, so a long GPU call no longer blocks the event loop (the reference's
 handlers are `async def` but fully blocking, app.py:187).
@@ -18,7 +20,7 @@ import io
 from typing import Any, Dict, Optional
 
 import numpy as np
-from fastapi import FastAPI, HTTPException
+from fastapi import FastAPI, File, HTTPException, UploadFile
 from fastapi.middleware.cors import CORSMiddleware
 from PIL import Image
 from pydantic import BaseModel
@@ -192,32 +194,52 @@ def process_all_levels(request: FilterRequest):
             profiling = check_ncu_available()
         results: Dict[str, FilterResponse] = {}
         for level in (1, 2):
-            result = _apply(request, img.copy(), level)
-            metrics: Dict[str, Any] = {"time_ms": float(result["time_ms"]), "bandwidth_gbps": float(result["bandwidth_gbps"]),
-                                       "fps": float(result["fps"])}
-            if profiling:
-                try:
-                    from ..profiling import get_common_ncu_metrics, profile_kernel_with_ncu
-                    ncu = profile_kernel_with_ncu(img.copy(), request.filter, level,
-                                                  request.sigma if request.filter == "gaussian" else None,
-                                                  request.radius if request.filter in ("gaussian", "box") else None)
-                    common = get_common_ncu_metrics(ncu, ncu_data=ncu)
-                    if common.get("time_ms", 0) > 0:
-                        metrics["ncu_profiled_time_ms"] = common["time_ms"]
-                    metrics.update({k: v for k, v in common.items() if k != "time_ms"})   # CUDA-event time stays primary
-                    metrics["ncu_data"] = ncu
-                except Exception as e:
-                    metrics["profiling_error"] = str(e)
-            results[f"level_{level}"] = FilterResponse(processed_image=encode_image_to_base64(result["image"]),
-                                                       metrics=metrics, info=_info(request, level, img.shape, True))
+            try:
+                result = _apply(request, img.copy(), level)
+                metrics: Dict[str, Any] = {"time_ms": float(result["time_ms"]), "bandwidth_gbps": float(result["bandwidth_gbps"]),
+                                           "fps": float(result["fps"])}
+                if profiling:
+                    try:
+                        from ..profiling import get_common_ncu_metrics, profile_kernel_with_ncu
+                        ncu = profile_kernel_with_ncu(img.copy(), request.filter, level,
+                                                      request.sigma if request.filter == "gaussian" else None,
+                                                      request.radius if request.filter in ("gaussian", "box") else None)
+                        common = get_common_ncu_metrics(ncu, ncu_data=ncu)
+                        if common.get("time_ms", 0) > 0:
+                            metrics["ncu_profiled_time_ms"] = common["time_ms"]
+                        metrics.update({k: v for k, v in common.items() if k != "time_ms"})   # CUDA-event time stays primary
+                        metrics["ncu_data"] = ncu
+                    except Exception as e:
+                        metrics["profiling_error"] = str(e)
+                results[f"level_{level}"] = FilterResponse(processed_image=encode_image_to_base64(result["image"]),
+                                                           metrics=metrics, info=_info(request, level, img.shape, True))
+            except Exception as e:      # app.py:461-466: log, keep going with the other level
+                print(f"Error processing level {level}: {str(e)}")
+                continue
+        if not results:                 # app.py:468-475
+            raise HTTPException(status_code=500, detail="Failed to process image with any optimization level")
         h, w, c = img.shape
         return AllLevelsResponse(original_image=encode_image_to_base64(img), results=results,
-                                 image_info={"width": int(w), "height": int(h), "channels": int(c)},
+                                 image_info={"width": int(w), "height": int(h), "channels": int(c), "filter": request.filter,
+                                             "parameters": {"sigma": request.sigma if request.filter == "gaussian" else None,
+                                                            "radius": request.radius if request.filter in ("gaussian", "box") else None}},
                                  profiling_available=profiling)
-    except HTTPException:
-        raise
-    except Exception as e:
+    except Exception as e:              # every failure, HTTP errors included, leaves as 500 like the reference (app.py:493-494)
         raise HTTPException(status_code=500, detail=f"Processing failed: {str(e)}")
+
+
+@app.post("/api/upload")
+def upload_image(file: UploadFile = File(...)):
+    """Upload an image file, get it back base64-encoded (app.py:496-524)."""
+    try:
+        image = Image.open(io.BytesIO(file.file.read()))
+        if image.mode not in ("RGB", "L"):
+            image = image.convert("RGB")
+        arr = np.array(image)
+        return {"base64_image": encode_image_to_base64(arr), "width": image.width, "height": image.height,
+                "channels": len(arr.shape) if len(arr.shape) == 2 else arr.shape[2]}
+    except Exception as e:
+        raise HTTPException(status_code=500, detail=f"Upload failed: {str(e)}")
 
 
 if __name__ == "__main__":

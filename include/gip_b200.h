@@ -134,7 +134,10 @@ int gip_gaussian_weights(float* weights_out, int radius, float sigma);
 const char* gip_error_string(int err);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 int64_t gip_launch_count(void);
-/* Release cached pinned/device staging buffers of the host entry points and trim the stream-ordered scratch pool. */
+/* Memory the library retains between calls: (1) the host entry points' pinned + device staging buffers (sized for the
+ * largest call so far), (2) per device, a library-owned stream-ordered pool (cudaMemPoolCreate, release threshold
+ * unlimited) that serves the scratch of the two-kernel and general paths -- up to 1 GiB per call, kept at its high-water
+ * mark.  The device's default mempool is not touched.  gip_release_cache() frees (1) and trims (2) on the current device. */
 int gip_release_cache(void);
 /* "gip_b200 <version> sm_100a" */
 const char* gip_version(void);

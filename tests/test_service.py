@@ -87,3 +87,37 @@ def test_ncu_csv_parser_keeps_the_reference_shape():
     assert ncu_profiler.get_common_ncu_metrics({}) == {}
     with pytest.raises(ValueError):
         ncu_profiler.profile_kernel_with_ncu(np.zeros((4, 4, 3), np.uint8), "median", 1)
+
+
+def test_upload_route_returns_base64_and_shape():
+    """POST /api/upload (reference backend/app.py:496-524)."""
+    arr = synth.uniform(9, 13, 3, seed=3)
+    buf = io.BytesIO()
+    Image.fromarray(arr).save(buf, format="PNG")
+    r = client.post("/api/upload", files={"file": ("x.png", buf.getvalue(), "image/png")})
+    assert r.status_code == 200
+    j = r.json()
+    assert (j["width"], j["height"], j["channels"]) == (13, 9, 3)
+    assert np.array_equal(_decode(j["base64_image"]), arr)
+    gray = Image.fromarray(arr[:, :, 0])                 # mode "L" stays gray; "channels" is the reference's quirk (ndim)
+    buf = io.BytesIO(); gray.save(buf, format="PNG")
+    j = client.post("/api/upload", files={"file": ("g.png", buf.getvalue(), "image/png")}).json()
+    assert j["channels"] == 2
+    r = client.post("/api/upload", files={"file": ("x.png", b"not an image", "image/png")})
+    assert r.status_code == 500 and "Upload failed" in r.json()["detail"]
+
+
+def test_process_all_undecodable_image_is_500_like_the_reference():
+    r = client.post("/api/process-all", json={"image": "not-base64!!", "filter": "sobel"})
+    assert r.status_code == 500 and "Processing failed" in r.json()["detail"]        # app.py:493-494
+
+
+def test_ncu_parser_sums_band_launches_per_call():
+    """The host path cuts big images into row-band chunks (one launch each): durations and DRAM bytes are summed over the
+    launches of a call, not averaged per kernel name."""
+    rows = RAW.strip().split("\n")
+    text = "\n".join(rows[:2] + [rows[2]] * 6 + [rows[3]] * 6) + "\n"      # 3 calls x 2 chunks x (H, V)
+    m = ncu_profiler.parse_ncu_raw_csv(text, calls=3)
+    assert m["total_kernel_duration_ms"] == pytest.approx(2 * 0.221)
+    assert m["launches_per_call"] == {"gip_gauss_h<3, 3, 1>": 2.0, "gip_gauss_v<3>": 2.0}
+    assert m["memory"]["dram_bytes_per_call"] == pytest.approx(2 * (99.5 + 50 + 100 + 50) * 1e6)
