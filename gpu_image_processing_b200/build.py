@@ -28,19 +28,34 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _deps_mtime():
-    m = 0.0
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            if f.endswith((".cuh", ".h", ".inc")):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
-    return m
+_INC = None
 
 
-def _compile(src: str, force: bool, hdr_mtime: float) -> str:
+def _includes(path, seen):
+    """Files reachable from `path` through #include "..." (relative to the including file)."""
+    import re
+    global _INC
+    _INC = _INC or re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    with open(path) as f:
+        text = f.read()
+    for inc in _INC.findall(text):
+        _includes(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+
+
+def _deps_mtime(src_path):
+    """Newest mtime among a source file and everything it includes (headers, .inc tables)."""
+    seen = set()
+    _includes(src_path, seen)
+    return max(os.path.getmtime(p) for p in seen)
+
+
+def _compile(src: str, force: bool) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
     path = os.path.join(CSRC, src)
-    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_mtime):
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > _deps_mtime(path):
         return obj
     cmd = [NVCC, *ARCH, *CFLAGS, "-c", path, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,10 +69,9 @@ def _compile(src: str, force: bool, hdr_mtime: float) -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    hdr = _deps_mtime()
     srcs = sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, force, hdr), srcs))
+        objs = list(ex.map(lambda s: _compile(s, force), srcs))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,7 +1,7 @@
 // fast_gauss_r31.cu -- radius 31 instantiation of the two-kernel Gaussian (one translation unit per radius so that
 // they compile in parallel; see fast_gauss_impl.cuh).  Radius <= 15: rotating accumulators, unrolled 2R+1 times.
 // Radius >= 16: shift formulation, rolled loops.
-#include "fast_gauss_impl.cuh"
+#include "gauss_shift_impl.cuh"
 
 namespace gip {
 cudaError_t gauss_run_r31(const Job& job, cudaStream_t stream) { return run_radius<31, true>(job, stream); }

@@ -26,6 +26,7 @@
 // The FP32 pipe is the roofline: 2 * ((2R+1) + 2) packed-lane operations per byte.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include "common.cuh"
@@ -60,7 +61,15 @@ template <int R, int C> struct FCfg {
 
 struct FusedTiling {
     int strips, bands, band_rows;
+    int decoupled;      // 1: producers and consumers meet on named barriers per ring slot (full / empty), not __syncthreads
 };
+
+// Named barriers 1..3 = FULL[slot], 4..6 = EMPTY[slot] (0 is __syncthreads).  Producers arrive on FULL[s % 3] when the rows
+// of step s are in the FIFO and consumers wait there; consumers arrive on EMPTY[s % 3] when every row of step s has been
+// consumed (end of their iteration s + 2: they take whole blocks of 2R+1 <= K+1 rows) and producers wait there before
+// step s + 3 overwrites the slot.  Every barrier counts all threads of the CTA (arrivals + waiters).
+__device__ __forceinline__ void fbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFThreads) : "memory"); }
+__device__ __forceinline__ void fbar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kFThreads) : "memory"); }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -153,6 +162,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         stage_rows(0);
         stage_rows(1);
         for (int step = 0; step <= nsteps; step++) {
+            if (tl.decoupled && step == nsteps) break;
             if (step < nsteps) {
                 cp_async_wait<1>();                  // the rows of `step` have landed (the copies of step + 1 may be in flight)
                 __syncwarp();
@@ -178,6 +188,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     }
                     __syncwarp();
                 }
+                if (tl.decoupled && step >= 3) fbar_sync(4 + step % 3);      // the consumers are done with step - 3 (same slot)
                 if (rel < nrows_in) {
                     // ---- H pass of rows rel (low halves of every pair) and rel + 1 (high halves)
                     const uint32_t ringA = ring_s + (uint32_t)(((step % 3) * kFK + 2 * warp) * kFRingPitch + lane_base);
@@ -217,7 +228,8 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 __syncwarp();                        // every lane has read this buffer: refill it for step + 2
                 stage_rows(step + 2);
             }
-            __syncthreads();
+            if (tl.decoupled) fbar_arrive(1 + step % 3);
+            else __syncthreads();
         }
     } else {
         // ==================================== consumer warp ====================================
@@ -269,6 +281,10 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
             done += R2;
         };
         for (int step = 0; step <= nsteps; step++) {
+            if (tl.decoupled) {
+                if (step == 0) continue;
+                fbar_sync(1 + (step - 1) % 3);       // the rows of step - 1 are in the FIFO
+            }
             if (any) {
                 const int avail = (step * kFK < nrows_in) ? step * kFK : nrows_in;      // rows of the steps before this one
                 const int target = (avail == nrows_in) ? nrows_in : avail - avail % R2;
@@ -277,7 +293,8 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     else v_block(std::false_type{});
                 }
             }
-            __syncthreads();
+            if (!tl.decoupled) __syncthreads();
+            else if (step >= 2 && step + 1 <= nsteps - 1) fbar_arrive(4 + (step - 2) % 3);   // a producer waits for it at step + 1
         }
     }
 }
@@ -315,6 +332,8 @@ cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
     }
     tl.bands = (int)want;
     tl.band_rows = (int)((rows + tl.bands - 1) / tl.bands);
+    static const int coupled_env = [] { const char* e = getenv("GIP_GAUSS_COUPLED"); return e ? atoi(e) : 0; }();   // A/B runs
+    tl.decoupled = coupled_env ? 0 : 1;
     const int64_t tiles = per_band * tl.bands;
     if (tiles > 0x7fffffff) return cudaSuccess;          // two-kernel path
     gip_gauss_fused<R, C><<<(unsigned)tiles, kFThreads, Cfg::kSmem, stream>>>(job, tl);
