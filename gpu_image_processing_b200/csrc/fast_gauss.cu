@@ -63,8 +63,9 @@ cudaError_t launch_fast_gauss(const Job& job, cudaStream_t stream, bool* handled
         }
         if (err != cudaSuccess || *handled) return err;
     }
-    // radius <= 15: rotating accumulators; 16..31: shift formulation (measured on the B200: the rotating form is 10-25 %
-    // faster up to 15 -- fewer instructions per tap -- and does not fit the register file beyond)
+    // radius <= 15: rotating accumulators; 16..31: shift formulation.  Measured on the B200 (8K RGB): the rotating form is
+    // faster up to 14 (r = 8: 177 vs 200 us, r = 12: 239 vs 250 us), equal at 15 (293 us), and does not fit the register
+    // file beyond.
     typedef cudaError_t (*RunFn)(const Job&, cudaStream_t);
     static const RunFn run[32] = {nullptr,
                                   gauss_run_r01, gauss_run_r02, gauss_run_r03, gauss_run_r04, gauss_run_r05, gauss_run_r06,

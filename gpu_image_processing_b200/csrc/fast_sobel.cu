@@ -191,11 +191,16 @@ __global__ void __launch_bounds__(kThreads, 2)
 gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTiling tl) {
     constexpr bool kInt = kU8 || C == 1;
     constexpr bool kSlab = Slab<C, VB>::kUse;
+    // VB == 1: rows that are not 4-byte aligned (odd pitches, e.g. the reference's 3239-pixel RGB shape).  Loads are
+    // aligned words around the lane's bytes, funnel-shifted by the row's misalignment; a lane stores the aligned words
+    // that straddle its own bytes and its left neighbour's last ones (by shuffle).  Strips at the row ends go byte by byte.
+    constexpr bool kMis = VB == 1;
+    constexpr int VBe = kMis ? 4 : VB;
     __shared__ __align__(16) uint8_t slab_mem[kSlab ? 2 * Slab<C, VB>::kBytes * kWarpsPerBlock : 16];
     const uint32_t slab0 = smem_addr(slab_mem) + (uint32_t)((threadIdx.x >> 5) * 2 * Slab<C, VB>::kBytes);
     constexpr int NW = 2 * C;                 // words per lane and row
-    constexpr int NCH = 8 * C / VB;           // vector chunks per lane and row
-    constexpr int WPC = VB / 4;               // words per chunk
+    constexpr int NCH = 8 * C / VBe;          // vector chunks per lane and row
+    constexpr int WPC = VBe / 4;              // words per chunk
     const int lane = threadIdx.x & 31;
     long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (tile >= tl.tiles) return;
@@ -210,7 +215,8 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     const int64_t x0 = (int64_t)strip * kStripPixels - kLanePixels + kLanePixels * lane;    // first pixel of this lane
     const int64_t boff = x0 * C;
     const bool stores = lane >= 1 && lane <= 30;
-    const bool lane_inside = boff >= 0 && boff + 8 * C <= pitch;
+    // (misaligned rows: an interior lane also keeps the aligned words around its bytes inside the row)
+    const bool lane_inside = kMis ? (boff >= 4 && boff + 8 * C + 4 <= pitch) : (boff >= 0 && boff + 8 * C <= pitch);
     const bool edge = !__all_sync(0xffffffffu, lane_inside);    // first / last strips of a row: offsets, masks, predicates
 
     // Input rows Y0-1 .. Y1 of the tile, requested in order.  Rows Y0 .. Y1-1 are the band's own memory (one pointer,
@@ -275,8 +281,8 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
         if (kEdge) {
 #pragma unroll
             for (int k = 0; k < NCH; k++) {
-                const int64_t o = boff + VB * k;
-                const bool inside = o >= 0 && o + VB <= pitch;
+                const int64_t o = boff + VBe * k;
+                const bool inside = o >= 0 && o + VBe <= pitch;
                 coff[k] = inside ? (int)o : 0;
                 cvalid[k] = stores && inside;
             }
@@ -296,8 +302,34 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
         }
         auto load = [&](const uint8_t* row) {
             RowWords<C> r;
+            if constexpr (kMis) {
+                const uint8_t* a = row + boff;                         // the lane's first byte (outside the row in edge strips)
+                const unsigned mis = (unsigned)((uintptr_t)a & 3);
+                uint32_t aw[NW + 1];                                   // aligned words [a - mis, a - mis + 4 NW + 4)
+                if (!kEdge || lane_inside) {                           // (edge strips: all but the one or two lanes at the row's ends)
 #pragma unroll
-            for (int k = 0; k < NCH; k++) load_vec<VB>(&r.w[WPC * k], kEdge ? row + coff[k] : row + boff + VB * k);
+                    for (int j = 0; j <= NW; j++) aw[j] = __ldg(reinterpret_cast<const uint32_t*>(a - mis + 4 * j));
+                } else {
+#pragma unroll
+                    for (int j = 0; j <= NW; j++) {
+                        const int64_t o = boff - (int64_t)mis + 4 * j;   // row-relative position of aligned word j
+                        uint32_t v = 0;
+                        if (o >= 0 && o + 4 <= pitch) {
+                            v = __ldg(reinterpret_cast<const uint32_t*>(row + o));
+                        } else if (o + 4 > 0 && o < pitch) {           // touches a row end: only bytes of the row are read
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (o + b >= 0 && o + b < pitch) v |= (uint32_t)row[o + b] << (8 * b);
+                        }
+                        aw[j] = v;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NW; k++) r.w[k] = __funnelshift_r(aw[k], aw[k + 1], 8 * mis);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NCH; k++) load_vec<VBe>(&r.w[WPC * k], kEdge ? row + coff[k] : row + boff + VBe * k);
+            }
             return r;
         };
         auto emit = [&](const GrayRow<kInt>& T, const GrayRow<kInt>& M, const GrayRow<kInt>& Bt, int y) {
@@ -341,10 +373,44 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
                         if (c >= 2 && c < 62) stg128_stream(out - 32 * lane + 16 * c, v);
                     }
                 }
+            } else if constexpr (kMis) {
+                // aligned word k = bytes [4k - mo, 4k - mo + 4) of the lane: the left neighbour's last mo bytes lead word 0
+                const unsigned mo = (unsigned)((uintptr_t)out & 3);
+                const uint32_t left = __shfl_up_sync(0xffffffffu, w[NW - 1], 1);
+                // lanes whose aligned words lie inside the row and whose left neighbour holds real pixels store words; in
+                // edge strips the one or two lanes at the row's ends store their bytes one by one
+                const bool word_lane = !kEdge || (boff >= 8 * C && boff + 8 * C <= pitch);
+                if (word_lane) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const uint32_t v = __funnelshift_l(k == 0 ? left : w[k - 1], w[k], 8 * mo);
+                        // lane 31 (halo) only completes the word that holds lane 30's last bytes; its own leading bytes are
+                        // pixel 0 of the next strip's lane 1, which writes the same values
+                        if (stores || (lane == 31 && k == 0 && mo != 0)) stg32_stream(out - mo + 4 * k, v);
+                    }
+                } else if (stores) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int64_t ob = boff + 4 * k + b;
+                            if (ob >= 0 && ob < pitch) out[4 * k + b] = (uint8_t)(w[k] >> (8 * b));
+                        }
+                }
+                if (kEdge && word_lane && stores) {
+                    // the lane's last mo bytes belong to the right neighbour's word 0: if that lane does not store words
+                    // (row end, or lane 31 of an edge strip), store them here
+                    const bool right_words = boff + 16 * C <= pitch && lane != 30;
+                    if (!right_words)
+                        for (unsigned b = 4 - mo; b < 4; b++) {
+                            const int64_t ob = boff + 4 * (NW - 1) + b;
+                            if (mo != 0 && ob < pitch) out[4 * (NW - 1) + b] = (uint8_t)(w[NW - 1] >> (8 * b));
+                        }
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < NCH; k++)
-                    if (kEdge ? cvalid[k] : stores) store_vec<VB>(out + VB * k, &w[WPC * k]);
+                    if (kEdge ? cvalid[k] : stores) store_vec<VBe>(out + VBe * k, &w[WPC * k]);
             }
             out += pitch;
         };
@@ -434,8 +500,7 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
                ((uintptr_t)job.out % a == 0) && (!job.src.above || (uintptr_t)job.src.above % a == 0) &&
                (!job.src.below || (uintptr_t)job.src.below % a == 0);
     };
-    // vector loads/stores: every row must start on a 4-byte boundary at least
-    if (!aligned(4)) return cudaSuccess;             // general path
+    const bool mis = !aligned(4);                     // rows at any byte alignment: the VB = 1 variants
     if (num_sms() <= 0) return cudaErrorInvalidDevice;
     SobelTiling tl;
     tl.strips = (int)((job.width + kStripPixels - 1) / kStripPixels);
@@ -443,6 +508,11 @@ cudaError_t launch_fast_sobel(const Job& job, cudaStream_t stream, bool* handled
     if (rows > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
     const int64_t per_band = (int64_t)tl.strips * job.batch;
     if (per_band > (int64_t)1 << 40) return cudaSuccess;
+    if (mis) {
+        if (C == 4) return launch_c<4, 1>(job, tl, per_band, rows, stream, handled);
+        if (C == 3) return launch_c<3, 1>(job, tl, per_band, rows, stream, handled);
+        return launch_c<1, 1>(job, tl, per_band, rows, stream, handled);
+    }
     if (C == 4) return aligned(16) ? launch_c<4, 16>(job, tl, per_band, rows, stream, handled) : launch_c<4, 4>(job, tl, per_band, rows, stream, handled);
     if (C == 3) return aligned(8) ? launch_c<3, 8>(job, tl, per_band, rows, stream, handled) : launch_c<3, 4>(job, tl, per_band, rows, stream, handled);
     return aligned(8) ? launch_c<1, 8>(job, tl, per_band, rows, stream, handled) : launch_c<1, 4>(job, tl, per_band, rows, stream, handled);

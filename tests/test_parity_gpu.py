@@ -499,3 +499,30 @@ def test_gaussian_wide_radii_fast_path(c, r, sigma):
     _check("gaussian", out.cpu().numpy(), O.gaussian_blur(img, sigma, r), f"wide gaussian bands c={c} r={r}")
     # two launches (H, V) per call on the fast path; the general path would also be two, so check the kernel is the fast one
     assert L.gip_launch_count() - before >= 2 * (6 + 1 + 4)
+
+
+def test_c1_shape_odd_pitch_sobel_and_box():
+    """The reference's README shape (3239 x 2146 RGB, 9717-byte rows: no row but the first is 4-byte aligned) through Sobel
+    and box blur: fast path == general path on the whole image, oracle on the top rows, an interior band, the bottom rows."""
+    import torch
+    from gpu_image_processing_b200 import device
+    L = _lib.load()
+    h, w, c = 2146, 3239, 3
+    img = synth.uniform(h, w, c, seed=11)
+    x = torch.from_numpy(img).cuda()
+    for kind, run, orc, r in (("sobel", lambda: device.sobel_edge_detection(x, 1), lambda s: O.sobel(s, 1), 1),
+                              ("sobel", lambda: device.sobel_edge_detection(x, 2), lambda s: O.sobel(s, 2), 1),
+                              ("box", lambda: device.box_blur(x, 3, 2), lambda s: O.box_blur(s, 3), 3),
+                              ("box", lambda: device.box_blur(x, 12, 1), lambda s: O.box_blur(s, 12), 12)):
+        fast = run().cpu().numpy()
+        old = L.gip_set_path(1)
+        try:
+            general = run().cpu().numpy()
+        finally:
+            L.gip_set_path(old)
+        assert np.array_equal(fast, general), kind
+        n = 40
+        _check(kind, fast[:n], orc(img[:n + r])[:n], f"c1-shape {kind} top rows")
+        _check(kind, fast[-n:], orc(img[-(n + r):])[-n:], f"c1-shape {kind} bottom rows")
+        y0 = h // 2
+        _check(kind, fast[y0:y0 + n], orc(img[y0 - r:y0 + n + r])[r:r + n], f"c1-shape {kind} interior rows")
