@@ -3,6 +3,8 @@
 // between the fused fast path and the general path, CUDA-event timing, host-buffer staging.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -394,6 +396,60 @@ static cudaError_t issue_compute(const HostPlan& p, HostCache& c, int64_t k) {
     return e;
 }
 
+// Persistent helper threads of the host path (created on first use, parked on a condition variable between calls:
+// spawning and tearing down eight threads per call cost ~0.3 ms, as much as the transfer of a 1080p frame).
+class HelperPool {
+  public:
+    // run fn(j) for j in [0, n) on pool threads; returns at once, wait() blocks until all have finished
+    void start(int n, std::function<void(int)> fn) {
+        std::unique_lock<std::mutex> lock(mu_);
+        while ((int)threads_.size() < n) {
+            const int id = (int)threads_.size();
+            threads_.emplace_back([this, id] { loop(id); });
+        }
+        fn_ = std::move(fn);
+        n_ = n; pending_ = n; generation_++;
+        cv_work_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_done_.wait(lock, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~HelperPool() {
+        { std::unique_lock<std::mutex> lock(mu_); stop_ = true; cv_work_.notify_all(); }
+        for (std::thread& t : threads_) t.join();
+    }
+  private:
+    void loop(int id) {
+        long seen = 0;
+        for (;;) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_work_.wait(lock, [&] { return stop_ || (generation_ != seen && id < n_); });
+                if (stop_) return;
+                seen = generation_;
+                fn = fn_;
+            }
+            fn(id);
+            std::unique_lock<std::mutex> lock(mu_);
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> fn_;
+    int n_ = 0, pending_ = 0;
+    long generation_ = 0;
+    bool stop_ = false;
+};
+static HelperPool* helper_pool() {
+    static HelperPool* pool = new HelperPool();      // leaked on purpose: no thread joins during process teardown
+    return pool;
+}
+
 // Pageable caller memory: helper threads copy slices of every chunk into / out of the pinned staging buffers
 // while the calling thread issues the kernels.  Progress is published through per-chunk atomics.
 struct HostProgress {
@@ -487,34 +543,44 @@ static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out
         // staging threads: split between the two directions, or all on the one direction that needs them
         const int t_in = pin_in ? 0 : (pin_out ? host_threads() : host_threads() / 2);
         const int t_out = pin_out ? 0 : (pin_in ? host_threads() : host_threads() - host_threads() / 2);
-        std::vector<std::thread> workers;
-        for (int j = 0; j < t_in; j++)
-            workers.emplace_back([&, j] {                          // stage slice j of every chunk; last one in uploads
-                cudaSetDevice(dev);
+        // helper j < t_in stages slice j of every chunk (the last one in uploads); helper j >= t_in drains slice j - t_in
+        helper_pool()->start(t_in + t_out, [&, t_in, t_out, dev, n](int j) {
+            cudaSetDevice(dev);
+            if (j < t_in) {
                 for (int64_t k = 0; k < n; k++) {
                     size_t a, b;
                     slice_of(p.len(k), j, t_in, &a, &b);
                     if (b > a) memcpy(c.p_in + p.off(k) + a, h_in + p.off(k) + a, b - a);
                     if (prog.staged[k].fetch_add(1, std::memory_order_acq_rel) == t_in - 1) {
                         if (k > 0) wait_flag(prog.uploaded[k - 1]);          // keep s_in in chunk order
+                        host_us[k] = host_now();                             // (GIP_VERBOSE timeline: staged, upload issued)
                         prog.fail(issue_upload(p, c, k));
                         prog.uploaded[k].store(1, std::memory_order_release);
                     }
                 }
-            });
-        for (int j = 0; j < t_out; j++)
-            workers.emplace_back([&, j] {                          // drain slice j of every chunk
-                cudaSetDevice(dev);
+                // Staging done: keep polling until the call's last download has landed.  Measured on the B200 box (64 MiB
+                // image, 8 helpers): when the helpers go to sleep as soon as the last chunk is staged, the remaining 3-4
+                // chunks crawl (4 MB copies take 0.6-1.0 ms instead of 0.1, band kernels 250 us instead of 40) and the call
+                // takes 3.6 ms; with the helpers polling it takes 2.4 ms (the pinned-buffer call: 2.05 ms).  4 pollers
+                // recover half of it.  GIP_HOST_SPIN=0 turns the polling off.
+                static const int spin_env = [] { const char* e = getenv("GIP_HOST_SPIN"); return e ? atoi(e) : 1; }();
+                if (spin_env) {
+                    wait_flag(prog.issued[n - 1]);
+                    while (prog.err.load() == 0 && cudaEventQuery(c.down[n - 1]) == cudaErrorNotReady) {}
+                }
+            } else {
+                const int jo = j - t_in;
                 for (int64_t k = 0; k < n; k++) {
                     wait_flag(prog.issued[k]);
                     if (prog.err.load() != 0) continue;
                     cudaError_t e = cudaEventSynchronize(c.down[k]);
                     if (e != cudaSuccess) { prog.fail(e); continue; }
                     size_t a, b;
-                    slice_of(p.len(k), j, t_out, &a, &b);
+                    slice_of(p.len(k), jo, t_out, &a, &b);
                     if (b > a) memcpy(h_out + p.off(k) + a, c.p_out + p.off(k) + a, b - a);
                 }
-            });
+            }
+        });
         for (int64_t k = 0; k < n; k++) {
             if (pin_in) {
                 prog.fail(issue_upload(p, c, k));
@@ -530,7 +596,7 @@ static cudaError_t run_host(FilterKind kind, const uint8_t* h_in, uint8_t* h_out
             if (prog.err.load() == 0) prog.fail(issue_compute(p, c, n - 1));
             prog.issued[n - 1].store(1, std::memory_order_release);
         }
-        for (std::thread& t : workers) t.join();
+        helper_pool()->wait();
         cudaError_t e1 = cudaStreamSynchronize(c.s_in), e2 = cudaStreamSynchronize(c.s_k), e3 = cudaStreamSynchronize(c.s_out);
         if (prog.err.load() != 0) return (cudaError_t)prog.err.load();
         if (e1 != cudaSuccess) return e1;
