@@ -49,7 +49,7 @@ FRAME_BYTES = FH * FW * FC
 FRAME_PIX = FH * FW
 G_SIGMA, G_RADIUS, B_RADIUS, S_LEVEL = 2.0, 3, 3, 1
 FILTERS = ("gaussian", "box", "sobel")
-KERNELS = {"gaussian": "gip_gauss_fused<3,3>", "box": "gip_box_fused<3,true,true,8>", "sobel": "gip_sobel_fused<3,false,*>"}
+KERNELS = {"gaussian": "gip_gauss_fused<3,3>", "box": "gip_box_fused<3,true,true,8>", "sobel": "gip_sobel_fused<3,false,8>"}
 E2E_FRAMES = 512
 C5 = dict(h=32768, w=32768, c=3, radius=15, sigma=5.0)
 C2 = dict(h=4096, w=4096, c=4, radii=list(range(1, 32)))

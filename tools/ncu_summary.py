@@ -6,7 +6,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum ', 'dram__bytes_write.su
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread ',
         'launch__grid_size', 'launch__block_size', 'launch__waves_per_multiprocessor', 'launch__occupancy_limit', 'smsp__inst_executed.sum ',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fmaheavy', 'sm__inst_executed_pipe_fmalite', 'sm__inst_executed_pipe_lsu.avg.pct',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg', 'sm__pipe_alu_cycles_active.avg', 'sm__pipe_fmaheavy_cycles_active.avg', 'sm__pipe_fmalite_cycles_active.avg', 'sm__inst_executed_pipe_fmaheavy', 'sm__inst_executed_pipe_fmalite', 'sm__inst_executed_pipe_lsu.avg.pct',
         'sm__inst_executed_pipe_xu.avg.pct', 'sm__inst_executed_pipe_uniform.avg.pct',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__average_warps_issue_stalled', 'sm__cycles_elapsed.max ', 'lts__t_bytes.sum ',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ', 'launch__shared_mem_per_block_dynamic', 'dram__throughput', 'lts__t_sectors_srcunit_tex_op_read.sum ', 'lts__t_sectors_srcunit_tex_op_write.sum ']
