@@ -498,6 +498,7 @@ def main():
               "halo_mode": "none" if world == 1 else "p2p: the kernels read the neighbours' halo rows through CUDA-IPC peer pointers over NVLink (no exchange step, no staging copy)",
               "halo_rows_per_side": 0 if world == 1 else r5,
               "halo_bytes_per_rank": 0 if world == 1 else (bi.plan.rows_above + bi.plan.rows_below) * W5 * C5c,
+              "halo_bytes_per_interior_rank": 0 if world <= 2 else 2 * r5 * W5 * C5c,
               "fp32": fp32_block(H5 * W5 * C5c / world, r5, ms5, None)}
         bi.finish()
         bi.close()
