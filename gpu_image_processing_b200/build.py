@@ -57,7 +57,7 @@ def _compile(src: str, force: bool) -> str:
     path = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > _deps_mtime(path):
         return obj
-    cmd = [NVCC, *ARCH, *CFLAGS, "-c", path, "-o", obj]
+    cmd = [NVCC, *ARCH, *CFLAGS, *os.environ.get("GIP_EXTRA_NVCC_FLAGS", "").split(), "-c", path, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".log", "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
