@@ -114,4 +114,38 @@ __device__ __forceinline__ uint32_t funnel_bytes(uint32_t lo, uint32_t hi, uint3
     return __funnelshift_r(lo, hi, shift_bits);
 }
 
+// Store one row segment at any byte alignment.  Lane l of a converged warp holds bytes [8l, 8l + 8) of a segment of
+// contiguous output bytes (w0 = the first four, little endian); p_lane = address of the lane's first byte; bytes
+// [seg_lo, seg_hi) of the segment exist and are this warp's to write, except that lane 0's own bytes are ALSO held by the
+// last lane of the warp to the left (the caller overlaps the warps by one lane).  Every lane >= 1 stores the ALIGNED
+// 8-byte word that ends inside its own bytes: its left neighbour's last mo bytes (by shuffle) followed by its own
+// first 8 - mo.  Lane 31's last mo bytes are left to the next warp (whose lane 0 repeats them), so no word is ever split
+// between warps; only words that straddle seg_lo / seg_hi (the ends of a strip or row) go out byte by byte.
+// seg_full = (seg_lo == 0 && seg_hi == 256): no range checks.  Nothing outside [seg_lo, seg_hi) is written.
+__device__ __forceinline__ void store_segment_dup(uint8_t* p_lane, uint32_t w0, uint32_t w1, int lane, int seg_lo, int seg_hi,
+                                                  bool seg_full) {
+    const unsigned mo = (unsigned)((uintptr_t)p_lane & 7);          // the same in every lane
+    uint32_t v0 = w0, v1 = w1;
+    if (mo != 0) {                                                   // warp-uniform branches
+        const uint32_t sh = 8u * ((8u - mo) & 3u);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, w1, 1);
+        if (mo <= 4) {            // V = bytes [8 - mo, 16 - mo) of the 16-byte sequence a b w0 w1
+            v0 = __funnelshift_r(b, w0, sh); v1 = __funnelshift_r(w0, w1, sh);
+        } else {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, w0, 1);
+            v0 = __funnelshift_r(a, b, sh); v1 = __funnelshift_r(b, w0, sh);
+        }
+    }
+    if (lane == 0) return;
+    uint8_t* q = p_lane - mo;
+    const int s = 8 * lane - (int)mo;                                // segment position of V's first byte
+    if (seg_full || (s >= seg_lo && s + 8 <= seg_hi)) {
+        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(q), "r"(v0), "r"(v1) : "memory");
+    } else if (s + 8 > seg_lo && s < seg_hi) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (s + k >= seg_lo && s + k < seg_hi) q[k] = (uint8_t)((k < 4 ? v0 : v1) >> (8 * (k & 3)));
+    }
+}
+
 }  // namespace gip

@@ -140,9 +140,14 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         // Buffer index i of the staged row holds image-row byte B0 + i.  direct: indices [0, sh + 1920) are real data
         // (clamp-to-edge outside the image).  scan: indices [0, sh) are zero (the leaving bytes of the warm-up zone),
         // [sh, sh + 1920) are real data.
+        // kVec: every row and buffer is 16-byte aligned, so the staged row's origin is fixed.  !kVec (rows at any byte
+        // alignment: odd pitches, unaligned base pointers): the origin moves with every row so that 16-byte chunks of
+        // global memory land on 16-byte chunks of shared memory (skew = (row address + B0) mod 16, see stage_row_any).
         const int skew = kVec ? (int)(((B0 % 16) + 16) % 16) : 0;
-        uint8_t* my_row = smem + (size_t)warp * tl.stage_row + 16 + skew;     // buffer index 0 of this warp's staged row
-        const uint32_t my_row_s = smem_addr(my_row);
+        uint8_t* const stage_base = smem + (size_t)warp * tl.stage_row;
+        const uint32_t stage_base_s = smem_addr(stage_base);
+        uint8_t* my_row = stage_base + 16 + skew;                             // buffer index 0 of this warp's staged row
+        uint32_t my_row_s = smem_addr(my_row);
         const int64_t first = kDirect ? B0 : e0;           // first image-row position the recurrence reads
         const int first_idx = kDirect ? 0 : sh;
         const int64_t lo = first < 0 ? 0 : first;
@@ -157,7 +162,6 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         const int ncopy = ce > cs ? (int)(ce - cs) : 0;
         const int nzero = (!kDirect && kVec && lo > cs) ? (int)(lo - cs) : 0;   // scan: bytes the aligned copy drops on the zero prefix
         const uint32_t copy_dst = my_row_s + (uint32_t)(int)(cs - B0) + 16u * lane;
-        uint8_t* copy_dst_g = my_row + (int)(cs - B0);
         // clamp-to-edge: positions [first, 0) (strip 0 only) and [pitch, pitch + rC) that fall inside the run;
         // the buffer origin and pitch are multiples of C there, so the channel of a replicated byte is its offset mod C.
         const int nleft = (first < 0) ? (int)(-first) : 0;                 // buffer indices [first_idx, first_idx + nleft)
@@ -171,7 +175,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         const bool edge_strip = nleft > 0 || nright > 0;
         const int64_t lane_off = cs + 16 * lane;
 
-        if (!kDirect)      // zero prefix: written once; the copies never touch it (but see nzero)
+        if (kVec && !kDirect)      // zero prefix: written once; the copies never touch it (but see nzero)
             for (int i = lane; i < sh; i += 32) my_row[i] = 0;
 
         // Row pointers advance by K rows inside the band's own memory and are recomputed at the seams (clamped
@@ -188,21 +192,56 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             if (rel < nrows_in) {
                 if (rel >= rel_fast_lo && rel < rel_fast_hi && gsrc != nullptr) gsrc += step_bytes;
                 else gsrc = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img) + lane_off;
-                if (kVec) {
+                {
                     if (c0) cp_async16(copy_dst, gsrc);
                     if (c1) cp_async16(copy_dst + 512, gsrc + 512);
                     if (c2) cp_async16(copy_dst + 1024, gsrc + 1024);
                     if (c3) cp_async16(copy_dst + 1536, gsrc + 1536);
-                } else {
-                    const uint8_t* src = gsrc - 16 * lane;
-                    for (int o = lane; o < ncopy; o += 32) copy_dst_g[o] = src[o];
                 }
             }
             cp_async_commit();
         };
+        // Rows at any alignment.  The whole 16-byte chunks of global memory that lie inside the row and touch [lo, hi) are
+        // copied with cp.async; the (at most 15 + 15, without a whole chunk at most 30) bytes of [lo, hi) before the
+        // first and after the last such chunk are loaded here, one per lane, and stored when the row is consumed.
+        // Strips that stay 15 bytes away from both row ends (`inner`) have neither and skip the clipping.
+        int st_skew = 0, st_nhead = 0, st_head_idx = 0, st_ntail = 0, st_tail_idx = 0;
+        uint32_t st_hb = 0, st_tb = 0;
+        const bool inner = lo >= 15 && hi + 15 <= pitch;
+        const int lo_i = (int)lo, hi_i = (int)hi, B0_i = (int)B0;      // row positions fit 31 bits (checked on the host)
+        const uint8_t* rowp = nullptr;
+        auto stage_row_any = [&](int rel) {
+            if (rel < nrows_in) {
+                if (rel >= rel_fast_lo && rel < rel_fast_hi && rowp != nullptr) rowp += step_bytes;
+                else rowp = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img);
+                const int a = (int)((uintptr_t)rowp & 15);
+                st_skew = (a + B0_i) & 15;
+                int p_lo = ((a + lo_i) & ~15) - a, p_hi = ((a + hi_i + 15) & ~15) - a;   // row positions the chunks cover
+                if (!inner) {
+                    if (p_lo < 0) p_lo += 16;
+                    if (p_hi > (int)pitch) p_hi -= 16;
+                    if (p_hi < p_lo) p_hi = p_lo;
+                    const int h_end = hi_i < p_lo ? hi_i : p_lo, t_beg = lo_i > p_hi ? lo_i : p_hi;
+                    st_nhead = h_end > lo_i ? h_end - lo_i : 0;
+                    st_ntail = hi_i > t_beg ? hi_i - t_beg : 0;
+                    st_head_idx = lo_i - B0_i;
+                    st_tail_idx = t_beg - B0_i;
+                    if (lane < st_nhead) st_hb = rowp[lo_i + lane];
+                    if (lane < st_ntail) st_tb = rowp[t_beg + lane];
+                }
+                const int nch = (p_hi - p_lo) >> 4;
+                const uint8_t* src = rowp + p_lo + 16 * lane;
+                const uint32_t dst = stage_base_s + 16u + (uint32_t)(st_skew + p_lo - B0_i) + 16u * lane;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (lane + 32 * q < nch) cp_async16(dst + 512 * q, src + 512 * q);
+            }
+            cp_async_commit();
+        };
+        auto stage_next = [&](int rel) {
+            if (kVec) stage_row(rel); else stage_row_any(rel);
+        };
 
-        const uint32_t aL = my_row_s + (uint32_t)(kLaneBytes * lane);
-        const uint32_t aE = aL + (uint32_t)sh;
         const uint32_t ring_lane = ring_s + (uint32_t)((lane - nw) * kLaneBytes);
 
         // direct mode: the window before a lane's run = its first sh leaving bytes = init_full whole 16-byte groups and
@@ -217,14 +256,26 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             init_mask[jj] = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
         }
 
-        stage_row(warp);
+        stage_next(warp);
         int slot = 0;                                      // ring slot of the step's first row
         for (int step = 0; step < nsteps; step++) {
             const int rel0 = step * K;
             if (rel0 + warp < nrows_in) {
                 cp_async_wait<0>();
-                if (!kDirect || edge_strip) __syncwarp();      // the fix-ups below touch bytes other lanes copied
-                if (nzero > 0 && lane < nzero) my_row[sh - nzero + lane] = 0;
+                if (!kVec || !kDirect || edge_strip) __syncwarp();      // the fix-ups below touch bytes other lanes copied
+                if (kVec) {
+                    if (nzero > 0 && lane < nzero) my_row[sh - nzero + lane] = 0;
+                } else {
+                    my_row = stage_base + 16 + st_skew;
+                    my_row_s = stage_base_s + 16u + (uint32_t)st_skew;
+                    if (!inner) {
+                        if (lane < st_nhead) my_row[st_head_idx + lane] = (uint8_t)st_hb;
+                        if (lane < st_ntail) my_row[st_tail_idx + lane] = (uint8_t)st_tb;
+                    }
+                    if (!kDirect)          // zero prefix (the chunk copies may have spilled into its last bytes)
+                        for (int i = lane; i < sh; i += 32) my_row[i] = 0;
+                    if (edge_strip) __syncwarp();
+                }
                 if (edge_strip) {
                     if (nleft > 0) {       // left image edge: replicate pixel 0
                         uint32_t e = 0;
@@ -243,7 +294,9 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
 
                 // leaving and entering words of this lane's run
                 uint32_t Lw[kLaneWords], Ew[kLaneWords];
-                if (C == 4) {
+                const uint32_t aL = my_row_s + (uint32_t)(kLaneBytes * lane);
+                const uint32_t aE = aL + (uint32_t)sh;
+                if (C == 4 && kVec) {
 #pragma unroll
                     for (int j = 0; j < kLaneWords; j++) { Lw[j] = lds32(aL + 4 * j); Ew[j] = lds32(aE + 4 * j); }
                 } else {
@@ -257,7 +310,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                     }
                 }
                 __syncwarp();
-                stage_row(rel0 + K + warp);    // the staged row is in registers: refill it for the next step
+                stage_next(rel0 + K + warp);   // the staged row is in registers: refill it for the next step
 
                 int acc[NACC];
                 if (kDirect) {
@@ -359,17 +412,31 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         // ==================================== consumer warp ====================================
         // Thread vt owns the GB-byte column group vt of the strip: one vector LDS per ring row, one vector STG per output
         // row, a warp covers 32 * GB contiguous bytes.
-        const int vt = tid - 32 * kHWarps;
+        // kVec: thread vt owns group vt.  Rows at any alignment (!kVec): a warp owns 31 groups and lane 0 repeats the last
+        // group of the warp before it, so that every lane >= 1 can store the ALIGNED 8-byte word that ends inside its own
+        // bytes (its left neighbour's last bytes come by shuffle) and no word is split between two warps; see
+        // store_segment_dup.  8 consumer warps x 31 groups cover the 240 groups of a strip.
         const int nvt = tl.useful / kGroupBytes;
+        const int vt = kVec ? tid - 32 * kHWarps : 31 * (warp - kHWarps) + lane - 1;
         const int64_t col = bxs + (int64_t)kGroupBytes * vt;
         int vbytes = 0;
-        if (vt < nvt && col < pitch) vbytes = (pitch - col >= kGroupBytes) ? kGroupBytes : (int)(pitch - col);
-        const bool any = vbytes > 0;
+        if (vt >= 0 && vt < nvt && col < pitch) vbytes = (pitch - col >= kGroupBytes) ? kGroupBytes : (int)(pitch - col);
+        const bool any_lane = vbytes > 0;
+        int seg_lo = 0, seg_hi = 0;                  // valid bytes of this warp's 32-group segment (position 0 = lane 0's first byte)
+        if (!kVec) {
+            const int64_t col0 = col - (int64_t)kGroupBytes * lane;
+            int64_t lim = bxs + tl.useful; if (lim > pitch) lim = pitch;
+            const int64_t v = lim - col0;
+            seg_hi = v < 0 ? 0 : (v > 32 * kGroupBytes ? 32 * kGroupBytes : (int)v);
+            seg_lo = (warp == kHWarps) ? kGroupBytes : 0;
+        }
+        const bool seg_full = seg_lo == 0 && seg_hi == 32 * kGroupBytes;
+        const bool any = kVec ? any_lane : seg_hi > seg_lo;
         uint32_t S[kGroupBytes];
 #pragma unroll
         for (int i = 0; i < kGroupBytes; i++) S[i] = kBias;
         uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;  // next output row
-        const uint32_t ring_tid = ring_s + (uint32_t)(kGroupBytes * (vt < nvt ? vt : 0));
+        const uint32_t ring_tid = ring_s + (uint32_t)(kGroupBytes * ((vt >= 0 && vt < nvt) ? vt : 0));
 
         auto v_row = [&](uint32_t a_in, uint32_t a_out, bool leave, bool store) {
             uint32_t iw[GW], ow[GW];
@@ -401,7 +468,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                     if (GB == 16) stg128_stream(optr, make_uint4(res[0], res[1], res[2 % GW], res[3 % GW]));
                     else stg64_stream(optr, res[0], res[1]);
                 } else {
-                    for (int b = 0; b < vbytes; b++) optr[b] = (uint8_t)(res[b >> 2] >> (8 * (b & 3)));
+                    store_segment_dup(optr, res[0], res[1 % GW], lane, seg_lo, seg_hi, seg_full);
                 }
                 optr += pitch;
             }
@@ -524,10 +591,11 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
                      ((uintptr_t)job.src.band % 16 == 0) && ((uintptr_t)job.out % 16 == 0) &&
                      (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
                      (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
+    if (!vec && pitch > 0x7fff0000) return cudaSuccess;  // the any-alignment path keeps row positions in 32 bits
     static const int coupled_env = [] { const char* e = getenv("GIP_BOX_COUPLED"); return e ? atoi(e) : 0; }();   // A/B runs
     tl.decoupled = coupled_env ? 0 : 1;
     static const int gb_env = [] { const char* e = getenv("GIP_BOX_GB"); return e ? atoi(e) : 0; }();   // A/B runs
-    const int gb = gb_env == 16 ? 16 : 8;
+    const int gb = (gb_env == 16 && vec) ? 16 : 8;       // rows at any alignment: 8-byte groups only
     cudaError_t err;
     if (gb == 16) err = C == 4 ? launch_c<4, 16>(job, tl, smem, tiles, vec, direct, stream)
                       : C == 3 ? launch_c<3, 16>(job, tl, smem, tiles, vec, direct, stream)
