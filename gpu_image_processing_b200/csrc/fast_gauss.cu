@@ -49,12 +49,9 @@ cudaError_t launch_fast_gauss(const Job& job, cudaStream_t stream, bool* handled
     if (job.src.band_y1 - job.src.band_y0 > 0x3fffffff || job.height > 0x3fffffff || pitch > 0x7fffffff) return cudaSuccess;
     if (num_sms() <= 0) return cudaErrorInvalidDevice;
     cudaError_t err;
-    // radius <= 4 on 16-byte aligned rows: one fused kernel, no scratch image (fused_gauss_impl.cuh)
+    // radius <= 4: one fused kernel, no scratch image, rows at any byte alignment (fused_gauss_impl.cuh)
     static const int no_fused = [] { const char* e = getenv("GIP_GAUSS_NO_FUSED"); return e ? atoi(e) : 0; }();   // A/B runs
-    const bool aligned16 = (pitch % 16 == 0) && (job.src.image_stride % 16 == 0) && ((uintptr_t)job.src.band % 16 == 0) &&
-                           ((uintptr_t)job.out % 16 == 0) && (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
-                           (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
-    if (r <= 4 && aligned16 && !no_fused) {
+    if (r <= 4 && !no_fused) {
         switch (r) {
             case 1: err = gauss_fused_r01(job, stream, handled); break;
             case 2: err = gauss_fused_r02(job, stream, handled); break;

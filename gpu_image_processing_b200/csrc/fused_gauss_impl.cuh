@@ -1,4 +1,4 @@
-// fused_gauss_impl.cuh -- single-kernel separable Gaussian blur for sm_100a, small radii, 16-byte aligned rows.
+// fused_gauss_impl.cuh -- single-kernel separable Gaussian blur for sm_100a, small radii, rows at any byte alignment.
 //
 // Replaces gaussianBlur{Horizontal,Vertical}{Naive,Level2} AND the d_temp image between them
 // (/root/reference/cuda_lib/src/image_filters.cu:64-144, :159-347, :759-761): the horizontally filtered, u8-rounded
@@ -24,6 +24,15 @@
 // Arithmetic is bit-identical to the reference: float32 weights from the host (image_filters.cu:25-39), one fmaf per
 // tap in tap order, (uchar)(sum + 0.5f) == low mantissa byte of RZ(RN(sum + 0.5f) + 2^23).
 // The FP32 pipe is the roofline: 2 * ((2R+1) + 2) packed-lane operations per byte.
+//
+// kAny = true (odd pitches, unaligned base pointers; the reference's 3239-pixel RGB README shape): the same kernel, plus
+//   stage    the 16-byte chunks of GLOBAL memory that lie inside the row are copied (cp.async needs aligned addresses), so
+//            a staged row arrives shifted by a = row address mod 16; the producer warp shifts it back in place (two
+//            LDS.128, four funnel shifts, one STS.128 per chunk) and lanes fetch the up to 15 bytes at either end of the
+//            row that belong to no whole chunk.  Everything after that is the aligned code.
+//   store    output rows start at any address: a consumer warp owns 31 column groups and its lane 0 repeats the last
+//            group of the warp to its left, so every lane >= 1 stores the aligned 8-byte word that ends inside its own
+//            bytes (store_segment_dup, device_utils.cuh).  A strip is 1968 bytes (246 of the 8 x 31 groups).
 #pragma once
 #include <atomic>
 #include <cstdlib>
@@ -46,15 +55,22 @@ constexpr int kFRingPitch = kFStrip + kFStrip / 8;      // 2304: one pad chunk p
 // byte offset of byte `idx` of a row stored in the padded layout
 __host__ __device__ constexpr int padded_off(int idx) { return 16 * ((idx >> 4) + (idx >> 7)) + (idx & 15); }
 
-template <int R, int C> struct FCfg {
+template <int R, int C, bool kAny = false> struct FCfg {
     static constexpr int RC = R * C;
     static constexpr int kPad = (RC + 15) & ~15;                    // bytes staged to the left of the strip
     static constexpr int kDelta = kPad - RC;                        // a lane's first input byte inside its first chunk
     static constexpr int kRowBytes = kPad + kFStrip + kPad;         // staged bytes per row
     static constexpr int kRowChunks = kRowBytes / 16;
-    static constexpr int kStagePitch = 16 * (kRowChunks + (kRowChunks + 7) / 8);
+    // output bytes per strip.  kAny: 246 of the 8 x 31 = 248 column groups, so that the lane after a strip's last group exists
+    // (it stores that group's trailing bytes) and strips still start on multiples of 16
+    static constexpr int kUseful = kAny ? 1968 : kFStrip;
+    // kAny: only the chunks that the lanes with outputs inside the strip read are staged and shifted
+    static constexpr int kNeedChunks = kAny ? (kDelta + kFLane * ((kUseful + kFLane - 1) / kFLane) + 2 * RC + 15) / 16 : kRowChunks;
+    static constexpr int kWinBytes = 16 * kNeedChunks;              // staged (logical) bytes per row that are ever read or fixed up
+    static constexpr int kRawChunks = kNeedChunks + (kAny ? 1 : 0); // a row shifted by up to 15 bytes spans one more chunk
+    static constexpr int kStagePitch = 16 * (kRawChunks + (kRawChunks + 7) / 8);
     static constexpr int kLaneChunks = (kDelta + kFLane + 2 * RC + 15) / 16;   // chunks a lane reads per row
-    static constexpr int kCopyIters = (kRowChunks + 31) / 32;
+    static constexpr int kCopyIters = (kRawChunks + 31) / 32;
     static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kFRingRows * kFRingPitch;
     static_assert(kLaneChunks <= 8, "lane chunk addressing assumes at most 8 chunks");
 };
@@ -90,10 +106,41 @@ __device__ __forceinline__ uint64_t round_pair_f(uint64_t acc) {
     return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
 }
 
-template <int R, int C>
+// Shift a staged row left by a bytes (1..15), in place: logical chunk c = bytes [a, a + 16) of raw chunks c, c + 1.
+// Chunk lane + 32 it sits at padded offset 16 (lane + lane / 8) + 576 it.
+template <int NCH>
+__device__ __forceinline__ void realign_row(uint32_t row_s, int a, int lane) {
+    const int ws = a >> 2;
+    const uint32_t bs = 8u * (uint32_t)(a & 3);
+    const uint32_t pA = row_s + 16u * (uint32_t)(lane + (lane >> 3));
+    const uint32_t pB = row_s + 16u * (uint32_t)((lane + 1) + ((lane + 1) >> 3));
+#pragma unroll
+    for (int it = 0; it < (NCH + 31) / 32; it++) {
+        const bool on = (32 * it + 31 < NCH) || (lane + 32 * it < NCH);
+        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+        if (on) {
+            const uint4 A = lds128(pA + 576u * it);
+            const uint4 B = lds128(pB + 576u * it);
+            if (ws == 0) {
+                o0 = __funnelshift_r(A.x, A.y, bs); o1 = __funnelshift_r(A.y, A.z, bs); o2 = __funnelshift_r(A.z, A.w, bs); o3 = __funnelshift_r(A.w, B.x, bs);
+            } else if (ws == 1) {
+                o0 = __funnelshift_r(A.y, A.z, bs); o1 = __funnelshift_r(A.z, A.w, bs); o2 = __funnelshift_r(A.w, B.x, bs); o3 = __funnelshift_r(B.x, B.y, bs);
+            } else if (ws == 2) {
+                o0 = __funnelshift_r(A.z, A.w, bs); o1 = __funnelshift_r(A.w, B.x, bs); o2 = __funnelshift_r(B.x, B.y, bs); o3 = __funnelshift_r(B.y, B.z, bs);
+            } else {
+                o0 = __funnelshift_r(A.w, B.x, bs); o1 = __funnelshift_r(B.x, B.y, bs); o2 = __funnelshift_r(B.y, B.z, bs); o3 = __funnelshift_r(B.z, B.w, bs);
+            }
+        }
+        __syncwarp();
+        if (on) sts128(pA + 576u * it, o0, o1, o2, o3);
+    }
+    __syncwarp();
+}
+
+template <int R, int C, bool kAny>
 __global__ void __launch_bounds__(kFThreads, 1)
 gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTiling tl) {
-    using Cfg = FCfg<R, C>;
+    using Cfg = FCfg<R, C, kAny>;
     constexpr int RC = Cfg::RC, R2 = 2 * R + 1;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -110,7 +157,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
     const int64_t Ystart = Y0 - R;                   // first input row of the tile
     const int nrows_in = (int)(Y1 - Y0) + 2 * R;
     const int nsteps = (nrows_in + kFK - 1) / kFK;
-    const int64_t bxs = (int64_t)strip * kFStrip;    // first output byte of the strip
+    const int64_t bxs = (int64_t)strip * Cfg::kUseful;   // first output byte of the strip
     const int64_t A0 = bxs - Cfg::kPad;              // image-row byte position of staged byte 0 (16-byte aligned)
     const uint32_t stage_s = smem_addr(smem);
     const uint32_t ring_s = stage_s + (uint32_t)(2 * kFK * Cfg::kStagePitch);
@@ -131,8 +178,10 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         // clamp-to-edge: staged bytes left of image byte 0 (strip 0) and right of the last image byte
         const int nleft = A0 < 0 ? (int)(-A0) : 0;               // staged indices [0, nleft)
         const int64_t row_end_idx = pitch - A0;                  // staged index of the first byte past the row
-        const int nright = (row_end_idx < Cfg::kRowBytes) ? (int)((Cfg::kRowBytes - row_end_idx) < RC ? (Cfg::kRowBytes - row_end_idx) : RC) : 0;
+        const int nright = (row_end_idx < Cfg::kWinBytes) ? (int)((Cfg::kWinBytes - row_end_idx) < RC ? (Cfg::kWinBytes - row_end_idx) : RC) : 0;
         const bool edge_strip = nleft > 0 || nright > 0;
+        // kAny: the last whole chunk of a row can end up to 15 bytes before the row does
+        const bool edge_any = edge_strip || (kAny && row_end_idx < Cfg::kWinBytes + 16);
 
         const int64_t own_lo = job.src.band_y0 > 0 ? job.src.band_y0 : 0;
         const int64_t own_hi = job.src.band_y1 < job.height ? job.src.band_y1 : job.height;
@@ -140,17 +189,56 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         const int rel_fast_hi = (int)(own_hi - Ystart);
         const int64_t step_bytes = (int64_t)kFK * pitch;
         const uint8_t* gsrc[2] = {nullptr, nullptr};
+        // kAny: gsrc[q] is the row's first byte; the row's address mod 16 of (buffer, q) is kept in a byte of skpack
+        uint32_t skpack = 0;
+        const int A0_i = (int)A0, pitch_i = (int)pitch;          // row positions fit 31 bits (checked on the host)
         auto stage_rows = [&](int step) {                        // this warp's two rows of `step` into buffer step & 1
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int rel = step * kFK + 2 * warp + q;
                 if (rel < nrows_in) {
-                    if (rel >= rel_fast_lo && rel < rel_fast_hi && gsrc[q] != nullptr) gsrc[q] += step_bytes;
-                    else gsrc[q] = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img) + lane_src;
                     const uint32_t dst = stage_s + (uint32_t)(((step & 1) * kFK + 2 * warp + q) * Cfg::kStagePitch + lane_dst);
+                    if (!kAny) {
+                        if (rel >= rel_fast_lo && rel < rel_fast_hi && gsrc[q] != nullptr) gsrc[q] += step_bytes;
+                        else gsrc[q] = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img) + lane_src;
 #pragma unroll
-                    for (int k = 0; k < Cfg::kCopyIters; k++)
-                        if ((copy_mask >> k) & 1) cp_async16(dst + 576 * k, gsrc[q] + 512 * k);
+                        for (int k = 0; k < Cfg::kCopyIters; k++)
+                            if ((copy_mask >> k) & 1) cp_async16(dst + 576 * k, gsrc[q] + 512 * k);
+                    } else {
+                        if (rel >= rel_fast_lo && rel < rel_fast_hi && gsrc[q] != nullptr) gsrc[q] += step_bytes;
+                        else gsrc[q] = job.src.row(clamp64(Ystart + rel, 0, job.height - 1), img);
+                        const int a = (int)((uintptr_t)gsrc[q] & 15);
+                        // Chunks that straddle the row's first / last byte also hold bytes of the row before / after it.
+                        // That memory belongs to the same buffer unless the row is the first / last one of its buffer
+                        // (band, above or below), so the straddling chunks are copied whole (the foreign bytes are
+                        // overwritten by the clamp-to-edge fix-up or never read); only at a buffer's two ends are they
+                        // left out and the row's own bytes fetched one by one when the row is consumed (bit 4 / 5).
+                        uint32_t unsafe = 0;
+                        if (edge_any) {
+                            const int64_t y = clamp64(Ystart + rel, 0, job.height - 1);
+                            bool first, last;
+                            if (y < job.src.band_y0) { first = y == job.src.above_y0; last = y == job.src.band_y0 - 1; }
+                            else if (y >= job.src.band_y1) { first = y == job.src.band_y1; last = y + 1 >= (job.src.band_y1 + R < job.height ? job.src.band_y1 + R : job.height); }
+                            else { first = y == job.src.band_y0 && img == 0; last = y == job.src.band_y1 - 1 && img == job.batch - 1; }
+                            if (pitch_i < 64) first = last = true;
+                            unsafe = (first ? 16u : 0u) | (last ? 32u : 0u);
+                        }
+                        const int sh = 8 * (2 * (step & 1) + q);
+                        skpack = (skpack & ~(255u << sh)) | (((uint32_t)a | unsafe) << sh);
+                        // raw chunk c = global bytes [row + A0 - a + 16 c, +16)
+                        int c_first = 0, c_end = Cfg::kRawChunks;
+                        if (edge_any) {
+                            if (a - A0_i > 0) c_first = (a - A0_i + ((unsafe & 16u) ? 15 : 0)) >> 4;
+                            const int ce = (pitch_i - A0_i + a + ((unsafe & 32u) ? 0 : 15)) >> 4;
+                            if (ce < c_end) c_end = ce;
+                        }
+                        const uint8_t* src = gsrc[q] + (A0_i - a) + 16 * lane;
+#pragma unroll
+                        for (int k = 0; k < Cfg::kCopyIters; k++) {
+                            const int c = lane + 32 * k;
+                            if (c >= c_first && c < c_end) cp_async16(dst + 576 * k, src + 512 * k);
+                        }
+                    }
                 }
             }
             cp_async_commit();
@@ -169,6 +257,44 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 const int rel = step * kFK + 2 * warp;
                 const uint32_t rowA = stage_s + (uint32_t)(((step & 1) * kFK + 2 * warp) * Cfg::kStagePitch);
                 const uint32_t rowB = rowA + Cfg::kStagePitch;
+                if (kAny) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        if (rel + q < nrows_in) {
+                            const uint32_t row = q ? rowB : rowA;
+                            const uint32_t sk = skpack >> (8 * (2 * (step & 1) + q));
+                            const int a = (int)(sk & 15u);
+                            // first / last row of a buffer, edge strips: the row's bytes that no copied chunk covers
+                            int nhead = 0, ntail = 0, head_pos = 0, tail_pos = 0;
+                            uint32_t hb = 0, tb = 0;
+                            const bool bytes = edge_any && (sk & 48u) != 0;
+                            if (bytes) {
+                                const uint8_t* rowp = job.src.row(clamp64(Ystart + rel + q, 0, job.height - 1), img);
+                                int c_first = 0, c_end = Cfg::kRawChunks;
+                                if (a - A0_i > 0) c_first = (a - A0_i + ((sk & 16u) ? 15 : 0)) >> 4;
+                                const int ce = (pitch_i - A0_i + a + ((sk & 32u) ? 0 : 15)) >> 4;
+                                if (ce < c_end) c_end = ce;
+                                if (c_end < c_first) c_end = c_first;
+                                const int cov_lo = A0_i - a + 16 * c_first, cov_hi = A0_i - a + 16 * c_end;   // row positions
+                                const int win_lo = A0_i > 0 ? A0_i : 0;
+                                const int win_hi = (A0_i + Cfg::kWinBytes < pitch_i) ? A0_i + Cfg::kWinBytes : pitch_i;
+                                const int h_end = win_hi < cov_lo ? win_hi : cov_lo;
+                                tail_pos = win_lo > cov_hi ? win_lo : cov_hi;
+                                head_pos = win_lo;
+                                nhead = h_end > win_lo ? h_end - win_lo : 0;
+                                ntail = win_hi > tail_pos ? win_hi - tail_pos : 0;
+                                if (lane < nhead) hb = rowp[head_pos + lane];
+                                if (lane < ntail) tb = rowp[tail_pos + lane];
+                            }
+                            if (a != 0) realign_row<Cfg::kNeedChunks>(row, a, lane);
+                            if (bytes) {
+                                if (lane < nhead) asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + padded_off(head_pos - A0_i + lane)), "r"(hb) : "memory");
+                                if (lane < ntail) asm volatile("st.shared.u8 [%0], %1;" ::"r"(row + padded_off(tail_pos - A0_i + lane)), "r"(tb) : "memory");
+                            }
+                        }
+                    }
+                    if (edge_any) __syncwarp();
+                }
                 if (edge_strip && rel < nrows_in) {
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
@@ -234,10 +360,21 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
     } else {
         // ==================================== consumer warp ====================================
         // Thread vt owns the 8-byte column group vt of the strip: 4 byte pairs, 2R+1 partial sums each.
-        const int vt = tid - 32 * kFProd;
+        // kAny: a warp owns 31 groups, lane 0 repeats the last group of the warp to its left (see store_segment_dup)
+        const int vt = kAny ? 31 * (warp - kFProd) + lane - 1 : tid - 32 * kFProd;
         const int64_t col = bxs + 8 * (int64_t)vt;
-        const bool any = col < pitch;                // pitch is a multiple of 16: a group is inside the row or outside it
-        const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vt >> 1) + (vt >> 4)) + 8 * (vt & 1));
+        int seg_lo = 0, seg_hi = 0;                  // kAny: valid bytes of this warp's 256-byte segment (position 0 = lane 0's first byte)
+        if (kAny) {
+            int64_t lim = bxs + Cfg::kUseful; if (lim > pitch) lim = pitch;
+            const int64_t v = lim - (col - 8 * lane);
+            seg_hi = v < 0 ? 0 : (v > 256 ? 256 : (int)v);
+            seg_lo = (warp == kFProd) ? 8 : 0;
+        }
+        const bool seg_full = seg_lo == 0 && seg_hi == 256;
+        // !kAny: pitch is a multiple of 16, so a group is inside the row or outside it
+        const bool any = kAny ? seg_hi > seg_lo : col < pitch;
+        const int vr = vt < 0 ? 0 : vt;              // (lane 0 of the first warp repeats nothing: it reads group 0 and stores nothing)
+        const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vr >> 1) + (vr >> 4)) + 8 * (vr & 1));
         uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;
         // Rows are consumed in blocks of 2R+1: inside a block the accumulator that takes tap k of row u is slot
         // (u - k) mod (2R+1), a compile-time register, and after a block every slot is back where it started -- no register
@@ -274,7 +411,8 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                         const uint64_t z0 = round_pair_f(acc[2 * h][(u + 1) % R2]), z1 = round_pair_f(acc[2 * h + 1][(u + 1) % R2]);
                         o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
                     }
-                    stg64_stream(optr, o[0], o[1]);
+                    if (kAny) store_segment_dup(optr, o[0], o[1], lane, seg_lo, seg_hi, seg_full);
+                    else stg64_stream(optr, o[0], o[1]);
                     optr += pitch;
                 }
             }
@@ -299,16 +437,16 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
     }
 }
 
-template <int R, int C>
+template <int R, int C, bool kAny>
 cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
-    using Cfg = FCfg<R, C>;
+    using Cfg = FCfg<R, C, kAny>;
     static std::atomic<bool> attr_set[64];           // per instantiation and per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_set[dev]) {
-        e = cudaFuncSetAttribute(gip_gauss_fused<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        e = cudaFuncSetAttribute(gip_gauss_fused<R, C, kAny>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
@@ -316,7 +454,7 @@ cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
     if (sms <= 0) return cudaErrorInvalidDevice;
     FusedTiling tl;
     const int64_t pitch = job.src.pitch;
-    tl.strips = (int)((pitch + kFStrip - 1) / kFStrip);
+    tl.strips = (int)((pitch + Cfg::kUseful - 1) / Cfg::kUseful);
     const int64_t rows = job.src.band_y1 - job.src.band_y0;
     // Row bands: the band count with the smallest (waves of resident CTAs) x (row steps of a tile: its rows, the 2R
     // rows that only fill the V accumulators, and the two-step pipeline fill).
@@ -336,7 +474,7 @@ cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
     tl.decoupled = coupled_env ? 0 : 1;
     const int64_t tiles = per_band * tl.bands;
     if (tiles > 0x7fffffff) return cudaSuccess;          // two-kernel path
-    gip_gauss_fused<R, C><<<(unsigned)tiles, kFThreads, Cfg::kSmem, stream>>>(job, tl);
+    gip_gauss_fused<R, C, kAny><<<(unsigned)tiles, kFThreads, Cfg::kSmem, stream>>>(job, tl);
     count_launch();
     e = cudaGetLastError();
     *handled = (e == cudaSuccess);
@@ -345,9 +483,20 @@ cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
 
 template <int R>
 cudaError_t run_fused_radius(const Job& job, cudaStream_t stream, bool* handled) {
-    if (job.channels == 4) return launch_fused<R, 4>(job, stream, handled);
-    if (job.channels == 3) return launch_fused<R, 3>(job, stream, handled);
-    return launch_fused<R, 1>(job, stream, handled);
+    const int64_t pitch = job.src.pitch;
+    const bool aligned16 = (pitch % 16 == 0) && (job.src.image_stride % 16 == 0) && ((uintptr_t)job.src.band % 16 == 0) &&
+                           ((uintptr_t)job.out % 16 == 0) && (!job.src.above || (uintptr_t)job.src.above % 16 == 0) &&
+                           (!job.src.below || (uintptr_t)job.src.below % 16 == 0);
+    if (aligned16) {
+        if (job.channels == 4) return launch_fused<R, 4, false>(job, stream, handled);
+        if (job.channels == 3) return launch_fused<R, 3, false>(job, stream, handled);
+        return launch_fused<R, 1, false>(job, stream, handled);
+    }
+    static const int no_any = [] { const char* e = getenv("GIP_GAUSS_NO_FUSED_ANY"); return e ? atoi(e) : 0; }();   // A/B runs
+    if (no_any || pitch > 0x7fff0000) return cudaSuccess;    // two-kernel path
+    if (job.channels == 4) return launch_fused<R, 4, true>(job, stream, handled);
+    if (job.channels == 3) return launch_fused<R, 3, true>(job, stream, handled);
+    return launch_fused<R, 1, true>(job, stream, handled);
 }
 
 }  // namespace
