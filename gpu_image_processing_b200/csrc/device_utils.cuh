@@ -114,6 +114,53 @@ __device__ __forceinline__ uint32_t funnel_bytes(uint32_t lo, uint32_t hi, uint3
     return __funnelshift_r(lo, hi, shift_bits);
 }
 
+// bytes [a, a + 16) of the 32-byte sequence A B (a = 0..15, the same in every lane: the branches are warp-uniform)
+__device__ __forceinline__ uint4 shift_chunk(const uint4& A, const uint4& B, int a) {
+    const int ws = a >> 2;
+    const uint32_t bs = 8u * (uint32_t)(a & 3);
+    uint4 o;
+    if (ws == 0) {
+        o.x = __funnelshift_r(A.x, A.y, bs); o.y = __funnelshift_r(A.y, A.z, bs); o.z = __funnelshift_r(A.z, A.w, bs); o.w = __funnelshift_r(A.w, B.x, bs);
+    } else if (ws == 1) {
+        o.x = __funnelshift_r(A.y, A.z, bs); o.y = __funnelshift_r(A.z, A.w, bs); o.z = __funnelshift_r(A.w, B.x, bs); o.w = __funnelshift_r(B.x, B.y, bs);
+    } else if (ws == 2) {
+        o.x = __funnelshift_r(A.z, A.w, bs); o.y = __funnelshift_r(A.w, B.x, bs); o.z = __funnelshift_r(B.x, B.y, bs); o.w = __funnelshift_r(B.y, B.z, bs);
+    } else {
+        o.x = __funnelshift_r(A.w, B.x, bs); o.y = __funnelshift_r(B.x, B.y, bs); o.z = __funnelshift_r(B.y, B.z, bs); o.w = __funnelshift_r(B.z, B.w, bs);
+    }
+    return o;
+}
+
+// A warp copies n bytes of a 16-byte aligned shared-memory row to global memory at ANY address: whole 16-byte stores at
+// the aligned addresses inside [dst, dst + n) (each is bytes [head + 16 j, +16) of the row: two LDS.128 and four funnel
+// shifts), the up to 15 bytes before the first and after the last of them one per lane.  The row must be readable up to
+// 16 bytes past n.  n <= 2048.
+__device__ __forceinline__ void flush_row_any(uint32_t row_s, uint8_t* dst, int n, int lane) {
+    int head = (int)((16u - (unsigned)((uintptr_t)dst & 15)) & 15u);
+    if (head > n) head = n;
+    const int nch = (n - head) >> 4;
+    const int tail0 = head + 16 * nch, ntail = n - tail0;
+    if (lane < head) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row_s + (uint32_t)lane));
+        dst[lane] = (uint8_t)v;
+    }
+    if (lane < ntail) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row_s + (uint32_t)(tail0 + lane)));
+        dst[tail0 + lane] = (uint8_t)v;
+    }
+    uint8_t* body = dst + head + 16 * lane;
+    const uint32_t src = row_s + 16u * (uint32_t)lane;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (lane + 32 * q < nch) {
+            const uint4 A = lds128(src + 512u * q), B = lds128(src + 512u * q + 16u);
+            stg128_stream(body + 512 * q, shift_chunk(A, B, head));
+        }
+    }
+}
+
 // Store one row segment at any byte alignment.  Lane l of a converged warp holds bytes [8l, 8l + 8) of a segment of
 // contiguous output bytes (w0 = the first four, little endian); p_lane = address of the lane's first byte; bytes
 // [seg_lo, seg_hi) of the segment exist and are this warp's to write, except that lane 0's own bytes are ALSO held by the

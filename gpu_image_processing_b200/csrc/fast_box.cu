@@ -103,9 +103,16 @@ __device__ __forceinline__ void stg64_stream(void* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int C, bool kVec, bool kDirect, int GB>
+// kMode 1: every row and buffer 16-byte aligned.  Rows at any byte alignment (odd pitches, unaligned base pointers):
+//   kMode 2  output rows return through shared memory: the consumers write them (8-byte STS, exactly the aligned kernel's
+//            work) into a double-buffered block of K rows after the ring, and one step later producer warp w stores row w
+//            with whole 16-byte stores at the aligned global addresses (flush_row_any).  The producers have the slack:
+//            with the stores on the consumer side (kMode 0) they sat on the EMPTY barrier for a third of their time.
+//   kMode 0  the consumers store themselves (store_segment_dup); only when the extra 60 KB do not fit (radius > 15).
+template <int C, int kMode, bool kDirect, int GB>
 __global__ void __launch_bounds__(box_threads(GB), 1)
 gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling tl) {
+    constexpr bool kVec = kMode == 1, kRet = kMode == 2;
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NACC = (C == 3) ? 3 : 4;
     constexpr int kGroupBytes = GB, GW = GB / 4;
@@ -132,6 +139,8 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
     const int64_t B0 = e0 - sh;                      // image-row byte position of buffer index 0
     const uint32_t ring_s = smem_addr(smem + (size_t)K * tl.stage_row);
     const int ring_bytes = tl.ring_rows * kRingPitch;
+    const uint32_t obuf_s = ring_s + (uint32_t)ring_bytes;        // kRet: 2 x K output rows (+ 16 bytes of slack)
+    const int nthreads = box_threads(GB);
     const uint32_t mag_a = c_box_magic[r].a_bits, mag_c = c_box_magic[r].c_bits;
     const uint64_t mag_a2 = pack_f2(mag_a, mag_a), mag_c2 = pack_f2(mag_c, mag_c);
 
@@ -256,6 +265,17 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             init_mask[jj] = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
         }
 
+        // kRet: store output row `warp` of consumer step s (named barriers 5, 6 = OUT_FULL[s & 1], 7, 8 = OUT_EMPTY[s & 1])
+        auto flush = [&](int s) {
+            bar_sync(5 + (s & 1), nthreads);
+            const int rel = s * K + warp;                      // the input row whose arrival completed this output row
+            if (rel >= 2 * r && rel < nrows_in) {
+                uint8_t* dst = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0 + (rel - 2 * r)) * pitch + bxs;
+                int64_t n = pitch - bxs; if (n > tl.useful) n = tl.useful;
+                flush_row_any(obuf_s + (uint32_t)(((s & 1) * K + warp) * kRingPitch), dst, (int)n, lane);
+            }
+            if (s + 2 < nsteps) bar_arrive(7 + (s & 1), nthreads);
+        };
         stage_next(warp);
         int slot = 0;                                      // ring slot of the step's first row
         for (int step = 0; step < nsteps; step++) {
@@ -406,7 +426,9 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             if (tl.decoupled) bar_arrive(1 + (step & 1), box_threads(GB));
             else __syncthreads();      // this step's rows are in the ring
             slot += K; if (slot >= tl.ring_rows) slot -= tl.ring_rows;
+            if (kRet && step >= 1) flush(step - 1);
         }
+        if (kRet) flush(nsteps - 1);
         if (!tl.decoupled) __syncthreads();          // matches the consumers' last barrier
     } else {
         // ==================================== consumer warp ====================================
@@ -417,13 +439,13 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         // bytes (its left neighbour's last bytes come by shuffle) and no word is split between two warps; see
         // store_segment_dup.  8 consumer warps x 31 groups cover the 240 groups of a strip.
         const int nvt = tl.useful / kGroupBytes;
-        const int vt = kVec ? tid - 32 * kHWarps : 31 * (warp - kHWarps) + lane - 1;
+        const int vt = (kVec || kRet) ? tid - 32 * kHWarps : 31 * (warp - kHWarps) + lane - 1;
         const int64_t col = bxs + (int64_t)kGroupBytes * vt;
         int vbytes = 0;
         if (vt >= 0 && vt < nvt && col < pitch) vbytes = (pitch - col >= kGroupBytes) ? kGroupBytes : (int)(pitch - col);
         const bool any_lane = vbytes > 0;
         int seg_lo = 0, seg_hi = 0;                  // valid bytes of this warp's 32-group segment (position 0 = lane 0's first byte)
-        if (!kVec) {
+        if (kMode == 0) {
             const int64_t col0 = col - (int64_t)kGroupBytes * lane;
             int64_t lim = bxs + tl.useful; if (lim > pitch) lim = pitch;
             const int64_t v = lim - col0;
@@ -431,14 +453,14 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             seg_lo = (warp == kHWarps) ? kGroupBytes : 0;
         }
         const bool seg_full = seg_lo == 0 && seg_hi == 32 * kGroupBytes;
-        const bool any = kVec ? any_lane : seg_hi > seg_lo;
+        const bool any = (kVec || kRet) ? any_lane : seg_hi > seg_lo;
         uint32_t S[kGroupBytes];
 #pragma unroll
         for (int i = 0; i < kGroupBytes; i++) S[i] = kBias;
         uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;  // next output row
         const uint32_t ring_tid = ring_s + (uint32_t)(kGroupBytes * ((vt >= 0 && vt < nvt) ? vt : 0));
 
-        auto v_row = [&](uint32_t a_in, uint32_t a_out, bool leave, bool store) {
+        auto v_row = [&](uint32_t a_in, uint32_t a_out, uint32_t a_o, bool leave, bool store) {
             uint32_t iw[GW], ow[GW];
             if (GB == 16) {
                 const uint4 in4 = lds128(a_in);
@@ -467,6 +489,8 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                 if (kVec) {
                     if (GB == 16) stg128_stream(optr, make_uint4(res[0], res[1], res[2 % GW], res[3 % GW]));
                     else stg64_stream(optr, res[0], res[1]);
+                } else if (kRet) {
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a_o), "r"(res[0]), "r"(res[1 % GW]) : "memory");
                 } else {
                     store_segment_dup(optr, res[0], res[1 % GW], lane, seg_lo, seg_hi, seg_full);
                 }
@@ -480,26 +504,28 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         for (int step = 0; step < nsteps; step++) {
             const int rel0 = step * K;
             if (tl.decoupled) bar_sync(1 + (step & 1), box_threads(GB));
+            if (kRet && step >= 2) bar_sync(7 + (step & 1), nthreads);      // the producers have stored the rows of step - 2
             if (any) {
                 uint32_t a_in = ring_tid + (uint32_t)(slot_in * kRingPitch);
                 uint32_t a_out = ring_tid + (uint32_t)(slot_out * kRingPitch);
+                uint32_t a_o = obuf_s + (uint32_t)((step & 1) * K * kRingPitch + kGroupBytes * vt);   // kRet: output row k of this step
                 const int wrap_out = tl.ring_rows - slot_out;          // first k whose leaving slot wraps
                 if (rel0 >= 2 * r + 1 && rel0 + K <= nrows_in) {
                     // steady state: every row has a leaving row and produces an output row
                     if (wrap_out >= K) {
 #pragma unroll
-                        for (int k = 0; k < K; k++) v_row(a_in + k * kRingPitch, a_out + k * kRingPitch, true, true);
+                        for (int k = 0; k < K; k++) v_row(a_in + k * kRingPitch, a_out + k * kRingPitch, a_o + k * kRingPitch, true, true);
                     } else {
 #pragma unroll 1
                         for (int k = 0; k < wrap_out; k++) {
-                            v_row(a_in, a_out, true, true);
-                            a_in += kRingPitch; a_out += kRingPitch;
+                            v_row(a_in, a_out, a_o, true, true);
+                            a_in += kRingPitch; a_out += kRingPitch; a_o += kRingPitch;
                         }
                         a_out -= (uint32_t)ring_bytes;
 #pragma unroll 1
                         for (int k = wrap_out; k < K; k++) {
-                            v_row(a_in, a_out, true, true);
-                            a_in += kRingPitch; a_out += kRingPitch;
+                            v_row(a_in, a_out, a_o, true, true);
+                            a_in += kRingPitch; a_out += kRingPitch; a_o += kRingPitch;
                         }
                     }
                 } else {
@@ -509,11 +535,12 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
 #pragma unroll 1
                     for (int k = 0; k < nk; k++) {
                         if (k == wrap_out) a_out -= (uint32_t)ring_bytes;
-                        v_row(a_in, a_out, k >= k_leave, k >= k_store);
-                        a_in += kRingPitch; a_out += kRingPitch;
+                        v_row(a_in, a_out, a_o, k >= k_leave, k >= k_store);
+                        a_in += kRingPitch; a_out += kRingPitch; a_o += kRingPitch;
                     }
                 }
             }
+            if (kRet) bar_arrive(5 + (step & 1), nthreads);          // this step's output rows are in shared memory
             if (!tl.decoupled) __syncthreads();      // the producers may overwrite this step's leaving rows; step+1 rows are ready
             else if (step + 2 < nsteps) bar_arrive(3 + (step & 1), box_threads(GB));
             slot_in += K; if (slot_in >= tl.ring_rows) slot_in -= tl.ring_rows;
@@ -522,7 +549,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
     }
 }
 
-template <int C, bool kVec, bool kDirect, int GB>
+template <int C, int kMode, bool kDirect, int GB>
 cudaError_t launch(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, cudaStream_t stream) {
     static std::atomic<bool> attr_set[64];   // per instantiation and per device: the opt-in is a per-device attribute
     int dev = 0;
@@ -530,19 +557,23 @@ cudaError_t launch(const Job& job, const BoxTiling& tl, size_t smem, int64_t til
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_set[dev]) {
-        e = cudaFuncSetAttribute(gip_box_fused<C, kVec, kDirect, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        e = cudaFuncSetAttribute(gip_box_fused<C, kMode, kDirect, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    gip_box_fused<C, kVec, kDirect, GB><<<(unsigned)tiles, box_threads(GB), smem, stream>>>(job, tl);
+    gip_box_fused<C, kMode, kDirect, GB><<<(unsigned)tiles, box_threads(GB), smem, stream>>>(job, tl);
     count_launch();
     return cudaGetLastError();
 }
 
-template <int C, int GB>
-cudaError_t launch_c(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, bool vec, bool direct, cudaStream_t stream) {
-    if (direct) return vec ? launch<C, true, true, GB>(job, tl, smem, tiles, stream) : launch<C, false, true, GB>(job, tl, smem, tiles, stream);
-    return vec ? launch<C, true, false, GB>(job, tl, smem, tiles, stream) : launch<C, false, false, GB>(job, tl, smem, tiles, stream);
+// mode: 1 aligned, 2 any alignment with the producers storing, 0 any alignment with the consumers storing
+template <int C>
+cudaError_t launch_c(const Job& job, const BoxTiling& tl, size_t smem, int64_t tiles, int mode, int gb, bool direct, cudaStream_t stream) {
+    if (mode == 1 && gb == 16)
+        return direct ? launch<C, 1, true, 16>(job, tl, smem, tiles, stream) : launch<C, 1, false, 16>(job, tl, smem, tiles, stream);
+    if (mode == 1) return direct ? launch<C, 1, true, 8>(job, tl, smem, tiles, stream) : launch<C, 1, false, 8>(job, tl, smem, tiles, stream);
+    if (mode == 2) return direct ? launch<C, 2, true, 8>(job, tl, smem, tiles, stream) : launch<C, 2, false, 8>(job, tl, smem, tiles, stream);
+    return direct ? launch<C, 0, true, 8>(job, tl, smem, tiles, stream) : launch<C, 0, false, 8>(job, tl, smem, tiles, stream);
 }
 
 }  // namespace
@@ -596,13 +627,15 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     tl.decoupled = coupled_env ? 0 : 1;
     static const int gb_env = [] { const char* e = getenv("GIP_BOX_GB"); return e ? atoi(e) : 0; }();   // A/B runs
     const int gb = (gb_env == 16 && vec) ? 16 : 8;       // rows at any alignment: 8-byte groups only
-    cudaError_t err;
-    if (gb == 16) err = C == 4 ? launch_c<4, 16>(job, tl, smem, tiles, vec, direct, stream)
-                      : C == 3 ? launch_c<3, 16>(job, tl, smem, tiles, vec, direct, stream)
-                               : launch_c<1, 16>(job, tl, smem, tiles, vec, direct, stream);
-    else          err = C == 4 ? launch_c<4, 8>(job, tl, smem, tiles, vec, direct, stream)
-                      : C == 3 ? launch_c<3, 8>(job, tl, smem, tiles, vec, direct, stream)
-                               : launch_c<1, 8>(job, tl, smem, tiles, vec, direct, stream);
+    // rows at any alignment: the producers store (mode 2) when the double-buffered block of output rows fits next to the ring
+    static const int no_ret = [] { const char* e = getenv("GIP_BOX_NO_RETURN"); return e ? atoi(e) : 0; }();   // A/B runs
+    const size_t smem_ret = smem + (size_t)2 * K * kRingPitch + 16;
+    const bool ret = !vec && tl.decoupled && !no_ret && smem_ret <= (size_t)kSmemLimit;
+    const int mode = vec ? 1 : (ret ? 2 : 0);
+    const size_t smem_used = ret ? smem_ret : smem;
+    cudaError_t err = C == 4 ? launch_c<4>(job, tl, smem_used, tiles, mode, gb, direct, stream)
+                    : C == 3 ? launch_c<3>(job, tl, smem_used, tiles, mode, gb, direct, stream)
+                             : launch_c<1>(job, tl, smem_used, tiles, mode, gb, direct, stream);
     *handled = (err == cudaSuccess);
     return err;
 }
