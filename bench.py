@@ -267,6 +267,9 @@ def other_configs(torch, device_mod, peak):
 
     for name, (h, w, c), nb, call in (
             ("c1_gaussian_3239x2146_rgb_s2_r3", (2146, 3239, 3), 8, lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 2, out=y)),
+            # the same odd-pitch shape (9717-byte rows) through the other two filters: the any-alignment paths
+            ("c1_shape_box_r3_odd_pitch", (2146, 3239, 3), 8, lambda x, y: device_mod.box_blur(x, 3, 2, out=y)),
+            ("c1_shape_sobel_odd_pitch", (2146, 3239, 3), 8, lambda x, y: device_mod.sobel_edge_detection(x, 1, out=y)),
             ("c3_sobel_7680x4320_rgb", (4320, 7680, 3), 3, lambda x, y: device_mod.sobel_edge_detection(x, 1, out=y)),
             ("c3_shape_gaussian_s2_r3", (4320, 7680, 3), 3, lambda x, y: device_mod.gaussian_blur(x, 2.0, 3, 1, out=y)),
             ("c3_shape_box_r3", (4320, 7680, 3), 3, lambda x, y: device_mod.box_blur(x, 3, 2, out=y)),

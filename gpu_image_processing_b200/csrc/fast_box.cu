@@ -34,6 +34,10 @@
 //           compile-time pitch, so a step's entering rows never wrap and its 16 rows are 16 LDS.128
 //           at immediate offsets; the leaving rows wrap at most once per step, at a row that is
 //           the same in every step (a step that wraps runs two short loops instead).
+// Rows at any byte alignment (odd pitches, unaligned base pointers) run the same kernel: see kMode at the kernel and
+// stage_row_any / flush_row_any -- chunks are copied from aligned global addresses into a staged row whose origin
+// moves with the row, and the output rows return through shared memory so that the producer warps can store them with
+// whole 16-byte stores at the aligned addresses.
 // Rounding.  The reference computes (uchar)(S*(1.0f/k)+0.5f) (:394, :429), which equals
 // floor((S+r)/k) for every S in [0,255k], k odd <= 63 (tests/test_oracle.py proves it
 // exhaustively).  Sums are kept as float bit patterns (2^23+S), and one FFMA2.RZ with per-radius

@@ -234,8 +234,14 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     const uint8_t* const p_last = job.src.row(clamp64(Y1, 0, H - 1), img);
     const uint8_t* rp = job.src.band + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch - pitch;   // "row Y0-1" of the band's memory
     int t_next = 0;                          // the next row of the band's own memory, relative to Y0
+#ifndef GIP_SOBEL_L2_AHEAD
+#define GIP_SOBEL_L2_AHEAD 0
+#endif
+    constexpr int kL2Ahead = GIP_SOBEL_L2_AHEAD;     // > 0: also pull the row that many rows further down into L2 (A/B knob)
     auto next_own_row = [&]() {              // rows Y0, Y0+1, ... ; from Y1 on: the last row, again and again
         rp = (t_next < nrows) ? rp + pitch : p_last;
+        if (kL2Ahead > 0 && t_next + kL2Ahead < nrows && lane_inside)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (int64_t)kL2Ahead * pitch + boff));
         t_next++;
         return rp;
     };

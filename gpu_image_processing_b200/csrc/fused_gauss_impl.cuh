@@ -112,15 +112,16 @@ template <int NCH>
 __device__ __forceinline__ void realign_row(uint32_t row_s, int a, int lane) {
     const int ws = a >> 2;
     const uint32_t bs = 8u * (uint32_t)(a & 3);
-    const uint32_t pA = row_s + 16u * (uint32_t)(lane + (lane >> 3));
-    const uint32_t pB = row_s + 16u * (uint32_t)((lane + 1) + ((lane + 1) >> 3));
-#pragma unroll
-    for (int it = 0; it < (NCH + 31) / 32; it++) {
-        const bool on = (32 * it + 31 < NCH) || (lane + 32 * it < NCH);
+    uint32_t pA = row_s + 16u * (uint32_t)(lane + (lane >> 3));
+    uint32_t pB = row_s + 16u * (uint32_t)((lane + 1) + ((lane + 1) >> 3));
+    // (rolled: the any-alignment kernel is bound by instruction fetch, every copy of this body counts)
+#pragma unroll 1
+    for (int it = 0; it < (NCH + 31) / 32; it++, pA += 576u, pB += 576u) {
+        const bool on = lane + 32 * it < NCH;
         uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
         if (on) {
-            const uint4 A = lds128(pA + 576u * it);
-            const uint4 B = lds128(pB + 576u * it);
+            const uint4 A = lds128(pA);
+            const uint4 B = lds128(pB);
             if (ws == 0) {
                 o0 = __funnelshift_r(A.x, A.y, bs); o1 = __funnelshift_r(A.y, A.z, bs); o2 = __funnelshift_r(A.z, A.w, bs); o3 = __funnelshift_r(A.w, B.x, bs);
             } else if (ws == 1) {
@@ -132,7 +133,7 @@ __device__ __forceinline__ void realign_row(uint32_t row_s, int a, int lane) {
             }
         }
         __syncwarp();
-        if (on) sts128(pA + 576u * it, o0, o1, o2, o3);
+        if (on) sts128(pA, o0, o1, o2, o3);
     }
     __syncwarp();
 }
@@ -258,7 +259,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 const uint32_t rowA = stage_s + (uint32_t)(((step & 1) * kFK + 2 * warp) * Cfg::kStagePitch);
                 const uint32_t rowB = rowA + Cfg::kStagePitch;
                 if (kAny) {
-#pragma unroll
+#pragma unroll 1
                     for (int q = 0; q < 2; q++) {
                         if (rel + q < nrows_in) {
                             const uint32_t row = q ? rowB : rowA;
