@@ -37,11 +37,6 @@ constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kLanePixels = 8;
 constexpr int kStripPixels = 30 * kLanePixels;       // 30 producing lanes
-#ifndef GIP_SOBEL_AHEAD
-#define GIP_SOBEL_AHEAD 3
-#endif
-constexpr int kAhead = GIP_SOBEL_AHEAD;              // rows of words in flight ahead of the stencil (a multiple of 3: the gray rows rotate in three slots)
-static_assert(kAhead % 3 == 0, "gray slots rotate mod 3");
 
 struct SobelTiling {
     int strips, bands, band_rows;
@@ -237,7 +232,8 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     // The words of three rows are in flight in registers; the row kL2Ahead rows further down is pulled into L2 at the same
     // time (one PREFETCH per lane and row), so that the register loads find it there instead of in HBM.  On the c4 frame
     // stream a quarter of all stall samples sat on the first use of a loaded row; measured 10.57 -> 9.75 ms per 4096 frames
-    // at distance 6 (3: 10.04, 9: 10.04, 14: 10.24; deeper REGISTER prefetch, GIP_SOBEL_AHEAD = 6, was slower: 11.0).
+    // at distance 6 (3: 10.04, 9: 10.04, 14: 10.24; six rows in flight in REGISTERS instead of three was slower: 11.0, and
+    // 126 registers).
 #ifndef GIP_SOBEL_L2_AHEAD
 #define GIP_SOBEL_L2_AHEAD 6
 #endif
@@ -432,22 +428,26 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
 
         // rows Y0-1 and Y0 prime the pipeline; the words of the next THREE rows are always in flight (three word
         // buffers rotate with the three gray rows, so nothing is copied between iterations)
-        GrayRow<kInt> G[3];
-        G[0] = make_gray<C, kU8>(load(p_first));
-        G[1] = make_gray<C, kU8>(load(next_own_row()));
-        RowWords<C> Wq[kAhead];
-#pragma unroll
-        for (int k = 0; k < kAhead; k++) Wq[k] = load(next_own_row());
-        for (int i = 0; i < nrows; i += kAhead) {
+        GrayRow<kInt> R0 = make_gray<C, kU8>(load(p_first));
+        GrayRow<kInt> R1 = make_gray<C, kU8>(load(next_own_row()));
+        GrayRow<kInt> R2;
+        RowWords<C> W0 = load(next_own_row());
+        RowWords<C> W1 = load(next_own_row());
+        RowWords<C> W2 = load(next_own_row());
+        for (int i = 0; i < nrows; i += 3) {
             const int y = y_first + i;
-#pragma unroll
-            for (int k = 0; k < kAhead; k++) {
-                if (k > 0 && i + k >= nrows) break;
-                // output row y + k needs rows y+k-1, y+k (gray slots k % 3, (k+1) % 3) and y+k+1 (Wq[k] -> slot (k+2) % 3)
-                G[(k + 2) % 3] = make_gray<C, kU8>(Wq[k]);
-                Wq[k] = load(next_own_row());
-                emit(G[k % 3], G[(k + 1) % 3], G[(k + 2) % 3], y + k);
-            }
+            // output row y needs rows y-1 (R0), y (R1), y+1 (W0 -> R2)
+            R2 = make_gray<C, kU8>(W0);
+            W0 = load(next_own_row());
+            emit(R0, R1, R2, y);
+            if (i + 1 >= nrows) break;
+            R0 = make_gray<C, kU8>(W1);
+            W1 = load(next_own_row());
+            emit(R1, R2, R0, y + 1);
+            if (i + 2 >= nrows) break;
+            R1 = make_gray<C, kU8>(W2);
+            W2 = load(next_own_row());
+            emit(R2, R0, R1, y + 2);
         }
     };
     if (edge) march(std::true_type{});
@@ -482,6 +482,8 @@ cudaError_t launch(const Job& job, SobelTiling tl, int64_t per_band, int64_t row
         const int64_t cost = waves * ((rows + nb - 1) / nb + 6);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bands = nb; }
     }
+    static const int bands_env = [] { const char* s = getenv("GIP_SOBEL_BANDS"); return s ? atoi(s) : 0; }();   // A/B runs
+    if (bands_env > 0 && bands_env <= max_bands) bands = bands_env;
     tl.bands = (int)bands;
     tl.band_rows = (int)((rows + bands - 1) / bands);
     tl.tiles = per_band * bands;
