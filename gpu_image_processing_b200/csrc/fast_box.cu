@@ -80,6 +80,8 @@ struct BoxTiling {
     int ring_rows;       // 2r+1+2K rounded up to a multiple of K
     int stage_row;       // bytes per staged row
     int decoupled;       // 1: producers and consumers meet on named barriers (full / empty per step parity), not __syncthreads
+    int ret;             // kMode 2: 1 = output rows return through shared memory (the producers store them); 0 = output rows are
+                         // 8-byte aligned (only the staging needs the per-row skew) and the consumers store them directly
 };
 
 // 4 window sums (float bit patterns) -> 4 rounded bytes packed in a word
@@ -430,9 +432,9 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
             if (tl.decoupled) bar_arrive(1 + (step & 1), box_threads(GB));
             else __syncthreads();      // this step's rows are in the ring
             slot += K; if (slot >= tl.ring_rows) slot -= tl.ring_rows;
-            if (kRet && step >= 1) flush(step - 1);
+            if (kRet && tl.ret && step >= 1) flush(step - 1);
         }
-        if (kRet) flush(nsteps - 1);
+        if (kRet && tl.ret) flush(nsteps - 1);
         if (!tl.decoupled) __syncthreads();          // matches the consumers' last barrier
     } else {
         // ==================================== consumer warp ====================================
@@ -494,7 +496,9 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                     if (GB == 16) stg128_stream(optr, make_uint4(res[0], res[1], res[2 % GW], res[3 % GW]));
                     else stg64_stream(optr, res[0], res[1]);
                 } else if (kRet) {
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a_o), "r"(res[0]), "r"(res[1 % GW]) : "memory");
+                    if (tl.ret) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a_o), "r"(res[0]), "r"(res[1 % GW]) : "memory");
+                    else if (vbytes == kGroupBytes) stg64_stream(optr, res[0], res[1 % GW]);
+                    else for (int b = 0; b < vbytes; b++) optr[b] = (uint8_t)(res[b >> 2] >> (8 * (b & 3)));
                 } else {
                     store_segment_dup(optr, res[0], res[1 % GW], lane, seg_lo, seg_hi, seg_full);
                 }
@@ -508,7 +512,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
         for (int step = 0; step < nsteps; step++) {
             const int rel0 = step * K;
             if (tl.decoupled) bar_sync(1 + (step & 1), box_threads(GB));
-            if (kRet && step >= 2) bar_sync(7 + (step & 1), nthreads);      // the producers have stored the rows of step - 2
+            if (kRet && tl.ret && step >= 2) bar_sync(7 + (step & 1), nthreads);      // the producers have stored the rows of step - 2
             if (any) {
                 uint32_t a_in = ring_tid + (uint32_t)(slot_in * kRingPitch);
                 uint32_t a_out = ring_tid + (uint32_t)(slot_out * kRingPitch);
@@ -544,7 +548,7 @@ gip_box_fused(const __grid_constant__ Job job, const __grid_constant__ BoxTiling
                     }
                 }
             }
-            if (kRet) bar_arrive(5 + (step & 1), nthreads);          // this step's output rows are in shared memory
+            if (kRet && tl.ret) bar_arrive(5 + (step & 1), nthreads);          // this step's output rows are in shared memory
             if (!tl.decoupled) __syncthreads();      // the producers may overwrite this step's leaving rows; step+1 rows are ready
             else if (step + 2 < nsteps) bar_arrive(3 + (step & 1), box_threads(GB));
             slot_in += K; if (slot_in >= tl.ring_rows) slot_in -= tl.ring_rows;
@@ -636,6 +640,7 @@ cudaError_t launch_fast_box(const Job& job, cudaStream_t stream, bool* handled) 
     const size_t smem_ret = smem + (size_t)2 * K * kRingPitch + 16;
     const bool ret = !vec && tl.decoupled && !no_ret && smem_ret <= (size_t)kSmemLimit;
     const int mode = vec ? 1 : (ret ? 2 : 0);
+    tl.ret = (pitch % 8 != 0 || job.src.image_stride % 8 != 0 || (uintptr_t)job.out % 8 != 0) ? 1 : 0;
     const size_t smem_used = ret ? smem_ret : smem;
     cudaError_t err = C == 4 ? launch_c<4>(job, tl, smem_used, tiles, mode, gb, direct, stream)
                     : C == 3 ? launch_c<3>(job, tl, smem_used, tiles, mode, gb, direct, stream)

@@ -61,9 +61,15 @@ template <int R, int C, bool kAny = false> struct FCfg {
     static constexpr int kDelta = kPad - RC;                        // a lane's first input byte inside its first chunk
     static constexpr int kRowBytes = kPad + kFStrip + kPad;         // staged bytes per row
     static constexpr int kRowChunks = kRowBytes / 16;
-    // output bytes per strip.  kAny: 246 of the 8 x 31 = 248 column groups, so that the lane after a strip's last group exists
-    // (it stores that group's trailing bytes) and strips still start on multiples of 16
-    static constexpr int kUseful = kAny ? 1968 : kFStrip;
+    // output bytes per strip.  kAny: 31 lanes' worth (1984 bytes), so that the block of output rows below fits next to the
+    // staging buffers and the FIFO
+    static constexpr int kUseful = kAny ? 31 * kFLane : kFStrip;
+    // kAny: output rows return through shared memory (the consumers write them with the aligned kernel's 8-byte store,
+    // the producers store them to global memory at the aligned addresses, flush_row_any).  One consumer iteration emits at
+    // most K + 2R rows (whole blocks of 2R+1 input rows).
+    static constexpr int kOutRows = kFK + 2 * R;
+    static constexpr int kOutPitch = kUseful;
+    static constexpr int kOutBytes = kAny ? kOutRows * kOutPitch + 16 : 0;
     // kAny: only the chunks that the lanes with outputs inside the strip read are staged and shifted
     static constexpr int kNeedChunks = kAny ? (kDelta + kFLane * ((kUseful + kFLane - 1) / kFLane) + 2 * RC + 15) / 16 : kRowChunks;
     static constexpr int kWinBytes = 16 * kNeedChunks;              // staged (logical) bytes per row that are ever read or fixed up
@@ -71,13 +77,16 @@ template <int R, int C, bool kAny = false> struct FCfg {
     static constexpr int kStagePitch = 16 * (kRawChunks + (kRawChunks + 7) / 8);
     static constexpr int kLaneChunks = (kDelta + kFLane + 2 * RC + 15) / 16;   // chunks a lane reads per row
     static constexpr int kCopyIters = (kRawChunks + 31) / 32;
-    static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kFRingRows * kFRingPitch;
+    static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kFRingRows * kFRingPitch + kOutBytes;
+    static_assert(kSmem <= 227 * 1024, "shared memory");
     static_assert(kLaneChunks <= 8, "lane chunk addressing assumes at most 8 chunks");
 };
 
 struct FusedTiling {
     int strips, bands, band_rows;
     int decoupled;      // 1: producers and consumers meet on named barriers per ring slot (full / empty), not __syncthreads
+    int ret;            // kAny: 1 = output rows return through shared memory and the producers store them; 0 = output rows are
+                        // 8-byte aligned (only the input needs the shift), the consumers store them themselves
 };
 
 // Named barriers 1..3 = FULL[slot], 4..6 = EMPTY[slot] (0 is __syncthreads).  Producers arrive on FULL[s % 3] when the rows
@@ -162,6 +171,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
     const int64_t A0 = bxs - Cfg::kPad;              // image-row byte position of staged byte 0 (16-byte aligned)
     const uint32_t stage_s = smem_addr(smem);
     const uint32_t ring_s = stage_s + (uint32_t)(2 * kFK * Cfg::kStagePitch);
+    const uint32_t obuf_s = ring_s + (uint32_t)(kFRingRows * kFRingPitch);      // kAny: the block of output rows
 
     if (warp < kFProd) {
         // ==================================== producer warp: rows 2*warp, 2*warp + 1 of every step ====================
@@ -248,10 +258,28 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         const int lane_base = 16 * (4 * lane + (lane >> 1));
         const int lane_base_hi = lane_base + 16 * (lane & 1);
 
+        // kAny: store the output rows of consumer iteration c (named barriers 7 = OUT_FULL, 8 = OUT_EMPTY).  The rows an
+        // iteration emits follow from the same arithmetic the consumers use: input rows [target(c-1), target(c)) are
+        // consumed, row rel >= 2R completes output row rel - 2R.
+        auto v_target = [&](int c) {
+            const int avail = (c * kFK < nrows_in) ? c * kFK : nrows_in;
+            return (avail == nrows_in) ? nrows_in : avail - avail % R2;
+        };
+        auto flush = [&](int c) {
+            fbar_sync(7);
+            const int lo = v_target(c - 1) > 2 * R ? v_target(c - 1) : 2 * R, hi = v_target(c);
+            int64_t n = pitch - bxs; if (n > Cfg::kUseful) n = Cfg::kUseful;
+            for (int i = warp; i < hi - lo; i += kFProd) {
+                uint8_t* dst = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0 + (lo - 2 * R) + i) * pitch + bxs;
+                flush_row_any(obuf_s + (uint32_t)(i * Cfg::kOutPitch), dst, (int)n, lane);
+            }
+            if (c + 1 <= nsteps) fbar_arrive(8);
+        };
         stage_rows(0);
         stage_rows(1);
         for (int step = 0; step <= nsteps; step++) {
             if (tl.decoupled && step == nsteps) break;
+            if (kAny && tl.ret && step >= 2) flush(step - 1);
             if (step < nsteps) {
                 cp_async_wait<1>();                  // the rows of `step` have landed (the copies of step + 1 may be in flight)
                 __syncwarp();
@@ -358,24 +386,20 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
             if (tl.decoupled) fbar_arrive(1 + step % 3);
             else __syncthreads();
         }
+        if (kAny && tl.ret) {
+            if (nsteps >= 2) flush(nsteps - 1);
+            flush(nsteps);
+        }
     } else {
         // ==================================== consumer warp ====================================
         // Thread vt owns the 8-byte column group vt of the strip: 4 byte pairs, 2R+1 partial sums each.
-        // kAny: a warp owns 31 groups, lane 0 repeats the last group of the warp to its left (see store_segment_dup)
-        const int vt = kAny ? 31 * (warp - kFProd) + lane - 1 : tid - 32 * kFProd;
+        const int vt = tid - 32 * kFProd;
         const int64_t col = bxs + 8 * (int64_t)vt;
-        int seg_lo = 0, seg_hi = 0;                  // kAny: valid bytes of this warp's 256-byte segment (position 0 = lane 0's first byte)
-        if (kAny) {
-            int64_t lim = bxs + Cfg::kUseful; if (lim > pitch) lim = pitch;
-            const int64_t v = lim - (col - 8 * lane);
-            seg_hi = v < 0 ? 0 : (v > 256 ? 256 : (int)v);
-            seg_lo = (warp == kFProd) ? 8 : 0;
-        }
-        const bool seg_full = seg_lo == 0 && seg_hi == 256;
-        // !kAny: pitch is a multiple of 16, so a group is inside the row or outside it
-        const bool any = kAny ? seg_hi > seg_lo : col < pitch;
-        const int vr = vt < 0 ? 0 : vt;              // (lane 0 of the first warp repeats nothing: it reads group 0 and stores nothing)
-        const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vr >> 1) + (vr >> 4)) + 8 * (vr & 1));
+        // !kAny: pitch is a multiple of 16, so a group is inside the row or outside it.  kAny: the last group of a row may
+        // be partial; its whole 8 bytes go to shared memory and the producers store the row's real length.
+        const bool any = col < pitch && 8 * vt < Cfg::kUseful;
+        const uint32_t ring_tid = ring_s + (uint32_t)(16 * ((vt >> 1) + (vt >> 4)) + 8 * (vt & 1));
+        uint32_t o_s = obuf_s + 8u * (uint32_t)vt;       // kAny: this thread's bytes of the next output row
         uint8_t* optr = job.out + img * job.src.image_stride + (Y0 - job.src.band_y0) * pitch + col;
         // Rows are consumed in blocks of 2R+1: inside a block the accumulator that takes tap k of row u is slot
         // (u - k) mod (2R+1), a compile-time register, and after a block every slot is back where it started -- no register
@@ -412,9 +436,13 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                         const uint64_t z0 = round_pair_f(acc[2 * h][(u + 1) % R2]), z1 = round_pair_f(acc[2 * h + 1][(u + 1) % R2]);
                         o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
                     }
-                    if (kAny) store_segment_dup(optr, o[0], o[1], lane, seg_lo, seg_hi, seg_full);
-                    else stg64_stream(optr, o[0], o[1]);
-                    optr += pitch;
+                    if (kAny && tl.ret) {
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(o_s), "r"(o[0]), "r"(o[1]) : "memory");
+                        o_s += Cfg::kOutPitch;
+                    } else {
+                        stg64_stream(optr, o[0], o[1]);
+                        optr += pitch;
+                    }
                 }
             }
             done += R2;
@@ -424,6 +452,10 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 if (step == 0) continue;
                 fbar_sync(1 + (step - 1) % 3);       // the rows of step - 1 are in the FIFO
             }
+            if (kAny && tl.ret) {
+                if (step >= 2) fbar_sync(8);         // the producers have stored the rows of the iteration before
+                o_s = obuf_s + 8u * (uint32_t)vt;
+            }
             if (any) {
                 const int avail = (step * kFK < nrows_in) ? step * kFK : nrows_in;      // rows of the steps before this one
                 const int target = (avail == nrows_in) ? nrows_in : avail - avail % R2;
@@ -432,6 +464,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     else v_block(std::false_type{});
                 }
             }
+            if (kAny && tl.ret) fbar_arrive(7);      // this iteration's output rows are in shared memory
             if (!tl.decoupled) __syncthreads();
             else if (step >= 2 && step + 1 <= nsteps - 1) fbar_arrive(4 + (step - 2) % 3);   // a producer waits for it at step + 1
         }
@@ -473,6 +506,7 @@ cudaError_t launch_fused(const Job& job, cudaStream_t stream, bool* handled) {
     tl.band_rows = (int)((rows + tl.bands - 1) / tl.bands);
     static const int coupled_env = [] { const char* e = getenv("GIP_GAUSS_COUPLED"); return e ? atoi(e) : 0; }();   // A/B runs
     tl.decoupled = coupled_env ? 0 : 1;
+    tl.ret = (kAny && (pitch % 8 != 0 || job.src.image_stride % 8 != 0 || (uintptr_t)job.out % 8 != 0)) ? 1 : 0;
     const int64_t tiles = per_band * tl.bands;
     if (tiles > 0x7fffffff) return cudaSuccess;          // two-kernel path
     gip_gauss_fused<R, C, kAny><<<(unsigned)tiles, kFThreads, Cfg::kSmem, stream>>>(job, tl);
@@ -494,7 +528,8 @@ cudaError_t run_fused_radius(const Job& job, cudaStream_t stream, bool* handled)
         return launch_fused<R, 1, false>(job, stream, handled);
     }
     static const int no_any = [] { const char* e = getenv("GIP_GAUSS_NO_FUSED_ANY"); return e ? atoi(e) : 0; }();   // A/B runs
-    if (no_any || pitch > 0x7fff0000) return cudaSuccess;    // two-kernel path
+    static const int coupled_any = [] { const char* e = getenv("GIP_GAUSS_COUPLED"); return e ? atoi(e) : 0; }();
+    if (no_any || coupled_any || pitch > 0x7fff0000) return cudaSuccess;    // two-kernel path (the any-alignment variant needs the named barriers)
     if (job.channels == 4) return launch_fused<R, 4, true>(job, stream, handled);
     if (job.channels == 3) return launch_fused<R, 3, true>(job, stream, handled);
     return launch_fused<R, 1, true>(job, stream, handled);

@@ -314,7 +314,7 @@ def test_host_pipeline_chunked_large_buffers(pin_in, pin_out):
         _check("sobel", got[i], O.sobel(frames[i], 2), f"frame {i}")
 
 
-@pytest.mark.parametrize("c,w", [(3, 323), (1, 1001), (3, 640), (4, 257), (1, 64), (3, 2501), (4, 1027), (1, 5003)])
+@pytest.mark.parametrize("c,w", [(3, 323), (1, 1001), (3, 640), (4, 257), (1, 64), (3, 2501), (4, 1027), (1, 5003), (3, 1000)])
 @pytest.mark.parametrize("shift", [0, 1, 2, 3, 5])
 def test_unaligned_buffers_and_canaries(c, w, shift, path):
     """Input and output at every byte alignment inside larger device buffers: the result still matches the oracle and
