@@ -198,6 +198,15 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     constexpr int VBe = kMis ? 4 : VB;
     __shared__ __align__(16) uint8_t slab_mem[kSlab ? 2 * Slab<C, VB>::kBytes * kWarpsPerBlock : 16];
     const uint32_t slab0 = smem_addr(slab_mem) + (uint32_t)((threadIdx.x >> 5) * 2 * Slab<C, VB>::kBytes);
+    // Rows at any alignment, strips inside the row: the warp's row segment (32 lanes x 8C bytes) is staged in shared
+    // memory with 16-byte cp.async from the aligned global chunks that cover it, kRingAhead rows ahead of the stencil, and a
+    // lane reads its own bytes from there (aligned LDS.32 + funnel shift).  The per-lane loads of the register path
+    // (seven lane-strided LDG.32 per row: every one touches 24 sectors) kept the L1 pipe busy and the warps waiting.
+    constexpr int kRingAhead = 4, kRingSlots = kRingAhead + 1;
+    constexpr int kSegChunks = (32 * 8 * C + 16) / 16;          // aligned 16-byte chunks that cover a segment at any alignment
+    constexpr int kSlotBytes = 32 * 8 * C + 32;
+    __shared__ __align__(16) uint8_t ring_mem[VB == 1 ? kRingSlots * kSlotBytes * kWarpsPerBlock : 16];
+    const uint32_t ring0 = smem_addr(ring_mem) + (uint32_t)((threadIdx.x >> 5) * kRingSlots * kSlotBytes);
     constexpr int NW = 2 * C;                 // words per lane and row
     constexpr int NCH = 8 * C / VBe;          // vector chunks per lane and row
     constexpr int WPC = VBe / 4;              // words per chunk
@@ -327,10 +336,13 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
                         uint32_t v = 0;
                         if (o >= 0 && o + 4 <= pitch) {
                             v = __ldg(reinterpret_cast<const uint32_t*>(row + o));
-                        } else if (o + 4 > 0 && o < pitch) {           // touches a row end: only bytes of the row are read
-#pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (o + b >= 0 && o + b < pitch) v |= (uint32_t)row[o + b] << (8 * b);
+                        } else if (o + 4 > 0 && o < pitch) {
+                            // Touches a row end.  The ALIGNED word that holds the row's first / last bytes is read whole: it
+                            // shares a 4-byte word (hence a page) with a byte of the row, and its foreign bytes only reach
+                            // border outputs, which are zero.  (Byte loads here -- up to 28 dependent ones per row in the one
+                            // or two lanes at a row's end -- made the edge strips' warps three times slower than the others,
+                            // and a launch is as slow as its slowest warp: 68 us on the c1 shape.)
+                            v = __ldg(reinterpret_cast<const uint32_t*>(row + o));
                         }
                         aw[j] = v;
                     }
@@ -426,6 +438,72 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
             out += pitch;
         };
 
+        if constexpr (kMis && !kEdge) {
+            // ---- shared-memory ring pipeline (see ring_mem)
+            const int64_t boff0 = boff - (int64_t)(8 * C) * lane;          // the segment's first byte in the row
+            uint32_t apack = 0;                                            // address mod 16 of the segment in each slot, 4 bits each
+            int s_put = 0, s_get = 0;
+            auto issue = [&](const uint8_t* row) {
+                const uint8_t* g0 = row + boff0;
+                const uint32_t a = (uint32_t)((uintptr_t)g0 & 15);
+                apack = (apack & ~(15u << (4 * s_put))) | (a << (4 * s_put));
+                const uint8_t* src = g0 - a + 16 * lane;
+                const uint32_t dst = ring0 + (uint32_t)(s_put * kSlotBytes + 16 * lane);
+                // (an aligned segment ends with its last whole chunk: every chunk copied holds bytes of the segment)
+                const int nch = kSegChunks - (a == 0 ? 1 : 0);
+#pragma unroll
+                for (int q = 0; q < (kSegChunks + 31) / 32; q++)
+                    if (lane + 32 * q < nch) cp_async16(dst + 512 * q, src + 512 * q);
+                cp_async_commit();
+                if (++s_put == kRingSlots) s_put = 0;
+            };
+            auto take = [&]() {
+                cp_async_wait<kRingAhead - 1>();
+                __syncwarp();
+                const uint32_t a = (apack >> (4 * s_get)) & 15u;
+                const uint32_t base = ring0 + (uint32_t)(s_get * kSlotBytes) + ((a + (uint32_t)(8 * C * lane)) & ~3u);
+                uint32_t aw[NW + 1];
+#pragma unroll
+                for (int j = 0; j <= NW; j++) aw[j] = lds32(base + 4 * j);
+                RowWords<C> r;
+#pragma unroll
+                for (int k = 0; k < NW; k++) r.w[k] = __funnelshift_r(aw[k], aw[k + 1], 8 * (a & 3u));
+                if (++s_get == kRingSlots) s_get = 0;
+                return r;
+            };
+            issue(p_first);
+#pragma unroll
+            for (int k = 1; k < kRingAhead; k++) issue(next_own_row());
+            GrayRow<kInt> R0 = make_gray<C, kU8>(take()); issue(next_own_row());
+            GrayRow<kInt> R1 = make_gray<C, kU8>(take()); issue(next_own_row());
+            // One copy of the row body (the gray rows move through registers instead of rotating by unrolling): the
+            // any-alignment variant is 2.8 x the aligned kernel's code and was starved by instruction fetch (1.6 stall
+            // cycles per issue with the inner and the edge march, 26 + 37 KB, resident on the same SM).
+#pragma unroll 1
+            for (int i = 0; i < nrows; i++) {
+                const GrayRow<kInt> R2 = make_gray<C, kU8>(take()); issue(next_own_row());
+                emit(R0, R1, R2, y_first + i);
+                R0 = R1; R1 = R2;
+            }
+            cp_async_wait<0>();
+            return;
+        }
+        if constexpr (kMis) {
+            // edge strips at any alignment: the per-lane loads, one copy of the row body as well
+            GrayRow<kInt> R0 = make_gray<C, kU8>(load(p_first));
+            GrayRow<kInt> R1 = make_gray<C, kU8>(load(next_own_row()));
+            RowWords<C> W0 = load(next_own_row());
+            RowWords<C> W1 = load(next_own_row());
+            RowWords<C> W2 = load(next_own_row());
+#pragma unroll 1
+            for (int i = 0; i < nrows; i++) {
+                const GrayRow<kInt> R2 = make_gray<C, kU8>(W0);
+                W0 = W1; W1 = W2; W2 = load(next_own_row());
+                emit(R0, R1, R2, y_first + i);
+                R0 = R1; R1 = R2;
+            }
+            return;
+        }
         // rows Y0-1 and Y0 prime the pipeline; the words of the next THREE rows are always in flight (three word
         // buffers rotate with the three gray rows, so nothing is copied between iterations)
         GrayRow<kInt> R0 = make_gray<C, kU8>(load(p_first));
@@ -474,7 +552,11 @@ cudaError_t launch(const Job& job, SobelTiling tl, int64_t per_band, int64_t row
     static const int warps_env = [] { const char* s = getenv("GIP_SOBEL_WARPS_PER_SM"); return s ? atoi(s) : 0; }();
     const int warps_per_sm = warps_env > 0 ? warps_env : per_sm * kWarpsPerBlock;
     const int64_t resident = (int64_t)num_sms() * warps_per_sm;
-    int64_t max_bands = rows / 24; if (max_bands < 1) max_bands = 1;  // a band re-reads 2 halo rows
+    // Shortest band: 12 rows (a band re-reads 2 halo rows and fills a 3-row pipeline).  It was 24 until the end of round 2,
+    // which left a 21 MB image (the c1 shape: 14 strips) with 1200 warps for 2368 resident ones: 22 -> 16 us aligned,
+    // 63 -> 42 us at odd pitch with 12; 8 is the same, 6 slower.
+    static const int min_band_rows = [] { const char* s = getenv("GIP_SOBEL_MIN_BAND_ROWS"); return s && atoi(s) > 0 ? atoi(s) : 12; }();   // A/B runs
+    int64_t max_bands = rows / min_band_rows; if (max_bands < 1) max_bands = 1;  // a band re-reads 2 halo rows
     if (max_bands > 1024) max_bands = 1024;
     int64_t bands = 1, best_cost = -1;
     for (int64_t nb = 1; nb <= max_bands; nb++) {

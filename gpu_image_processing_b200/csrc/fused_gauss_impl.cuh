@@ -30,9 +30,10 @@
 //            a staged row arrives shifted by a = row address mod 16; the producer warp shifts it back in place (two
 //            LDS.128, four funnel shifts, one STS.128 per chunk) and lanes fetch the up to 15 bytes at either end of the
 //            row that belong to no whole chunk.  Everything after that is the aligned code.
-//   store    output rows start at any address: a consumer warp owns 31 column groups and its lane 0 repeats the last
-//            group of the warp to its left, so every lane >= 1 stores the aligned 8-byte word that ends inside its own
-//            bytes (store_segment_dup, device_utils.cuh).  A strip is 1968 bytes (246 of the 8 x 31 groups).
+//   store    output rows start at any address: they return through shared memory -- the consumers write them with the
+//            aligned kernel's 8-byte store into a block of K + 2R rows behind the FIFO, then every consumer warp stores
+//            whole rows with 16-byte stores at the aligned global addresses (flush_row_any, device_utils.cuh).  A strip is
+//            1984 bytes (31 lanes) so that the block fits.  Output rows that are 8-byte aligned are stored directly.
 #pragma once
 #include <atomic>
 #include <cstdlib>
