@@ -134,7 +134,8 @@ __device__ __forceinline__ uint4 shift_chunk(const uint4& A, const uint4& B, int
 // A warp copies n bytes of a 16-byte aligned shared-memory row to global memory at ANY address: whole 16-byte stores at
 // the aligned addresses inside [dst, dst + n) (each is bytes [head + 16 j, +16) of the row: two LDS.128 and four funnel
 // shifts), the up to 15 bytes before the first and after the last of them one per lane.  The row must be readable up to
-// 16 bytes past n.  n <= 2048.
+// 16 bytes past n.  n <= 512 kQ (2048 by default).
+template <int kQ = 4>
 __device__ __forceinline__ void flush_row_any(uint32_t row_s, uint8_t* dst, int n, int lane) {
     int head = (int)((16u - (unsigned)((uintptr_t)dst & 15)) & 15u);
     if (head > n) head = n;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void flush_row_any(uint32_t row_s, uint8_t* dst, int 
     uint8_t* body = dst + head + 16 * lane;
     const uint32_t src = row_s + 16u * (uint32_t)lane;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < kQ; q++) {
         if (lane + 32 * q < nch) {
             const uint4 A = lds128(src + 512u * q), B = lds128(src + 512u * q + 16u);
             stg128_stream(body + 512 * q, shift_chunk(A, B, head));

@@ -207,6 +207,19 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
     constexpr int kSlotBytes = 32 * 8 * C + 32;
     __shared__ __align__(16) uint8_t ring_mem[VB == 1 ? kRingSlots * kSlotBytes * kWarpsPerBlock : 16];
     const uint32_t ring0 = smem_addr(ring_mem) + (uint32_t)((threadIdx.x >> 5) * kRingSlots * kSlotBytes);
+    // ... and their output rows leave the same way: a lane writes its 8C bytes to a per-warp slab (lane l at 8 + 8C l, so
+    // that lane 1's first byte sits on a 16-byte boundary) and the warp stores the 30 producing lanes' bytes with whole
+    // 16-byte stores at the aligned global addresses (flush_row_any).  The per-lane aligned-word stores this replaces
+    // (2C lane-strided STG.32 per row, each touching 24 sectors) were the L1 pipe's largest load after the input side went
+    // through the ring.  (RGBA rows are word-aligned whenever the buffer is: C == 4 keeps the word stores, the ring and two
+    // slabs of 1 KB rows would not fit the 48 KB of static shared memory.)
+#ifndef GIP_SOBEL_FLUSH
+#define GIP_SOBEL_FLUSH 1
+#endif
+    constexpr bool kFlush = VB == 1 && C != 4 && GIP_SOBEL_FLUSH != 0;
+    constexpr int kOSlab = 32 * 8 * C + 32;
+    __shared__ __align__(16) uint8_t oslab_mem[kFlush ? 2 * kOSlab * kWarpsPerBlock : 16];
+    const uint32_t oslab0 = smem_addr(oslab_mem) + (uint32_t)((threadIdx.x >> 5) * 2 * kOSlab);
     constexpr int NW = 2 * C;                 // words per lane and row
     constexpr int NCH = 8 * C / VBe;          // vector chunks per lane and row
     constexpr int WPC = VBe / 4;              // words per chunk
@@ -396,6 +409,16 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
                         if (c >= 2 && c < 62) stg128_stream(out - 32 * lane + 16 * c, v);
                     }
                 }
+            } else if constexpr (kFlush) {
+                const uint32_t slab = oslab0 + (uint32_t)((y & 1) * kOSlab);
+#pragma unroll
+                for (int k = 0; k < NW / 2; k++) sts64(slab + 8 + 8 * C * lane + 8 * k, w[2 * k], w[2 * k + 1]);
+                __syncwarp();
+                // out points at the lane's own bytes; lane 1's are the first of the 30 x 8C bytes this warp writes (the last
+                // strips of a row: as many of them as the row has)
+                int n = 30 * 8 * C;
+                if (kEdge) { const int64_t left = pitch - (boff - (int64_t)(8 * C) * (lane - 1)); if (left < n) n = left > 0 ? (int)left : 0; }
+                if (n > 0) flush_row_any<(30 * 8 * C + 511) / 512>(slab + 8 + 8 * C, out - 8 * C * (lane - 1), n, lane);
             } else if constexpr (kMis) {
                 // aligned word k = bytes [4k - mo, 4k - mo + 4) of the lane: the left neighbour's last mo bytes lead word 0
                 const unsigned mo = (unsigned)((uintptr_t)out & 3);
@@ -438,7 +461,7 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
             out += pitch;
         };
 
-        if constexpr (kMis && !kEdge) {
+        if constexpr (kMis && (!kEdge || kFlush)) {
             // ---- shared-memory ring pipeline (see ring_mem)
             const int64_t boff0 = boff - (int64_t)(8 * C) * lane;          // the segment's first byte in the row
             uint32_t apack = 0;                                            // address mod 16 of the segment in each slot, 4 bits each
@@ -452,8 +475,13 @@ gip_sobel_fused(const __grid_constant__ Job job, const __grid_constant__ SobelTi
                 // (an aligned segment ends with its last whole chunk: every chunk copied holds bytes of the segment)
                 const int nch = kSegChunks - (a == 0 ? 1 : 0);
 #pragma unroll
-                for (int q = 0; q < (kSegChunks + 31) / 32; q++)
-                    if (lane + 32 * q < nch) cp_async16(dst + 512 * q, src + 512 * q);
+                for (int q = 0; q < (kSegChunks + 31) / 32; q++) {
+                    // Edge strips: only the chunks that hold at least one byte of the row.  (Such an aligned chunk lies in a
+                    // page of the row's buffer; its foreign bytes -- and the stale bytes of the chunks left out -- only reach
+                    // border outputs, which are zero.)
+                    const bool in_row = !kEdge || (src + 512 * q + 16 > row && src + 512 * q < row + pitch);
+                    if (lane + 32 * q < nch && in_row) cp_async16(dst + 512 * q, src + 512 * q);
+                }
                 cp_async_commit();
                 if (++s_put == kRingSlots) s_put = 0;
             };

@@ -112,8 +112,40 @@ __device__ __forceinline__ void stg64_stream(void* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t byte_to_float_bits(uint32_t w, int b) {
     return u2f_bits(__byte_perm(w, 0u, 0x4440 | b));
 }
+// The same conversion as ONE instruction on the XU pipe (I2F.U8 with a byte selector, 16 lanes/clk/SM): a quarter of the
+// rate, but one issue slot instead of two and nothing on the ALU pipe.  Which bytes of a word take which route is a
+// compile-time mask per pass (bit b = byte b of every word goes through the XU pipe).
+#ifndef GIP_FUSED_XU_H
+#define GIP_FUSED_XU_H 0
+#endif
+#ifndef GIP_FUSED_XU_V
+#define GIP_FUSED_XU_V 0
+#endif
+template <int kMask>
+__device__ __forceinline__ uint32_t byte_to_float_bits_m(uint32_t w, int b) {
+    if ((kMask >> b) & 1) return __float_as_uint((float)((w >> (8 * b)) & 0xffu));
+    return byte_to_float_bits(w, b);
+}
 __device__ __forceinline__ uint64_t round_pair_f(uint64_t acc) {
     return add_rz_x2(add_rn_x2(acc, splat_f2(0.5f)), splat_f2(8388608.0f));
+}
+// The truncation as two F2I on the XU pipe instead of one packed add on the FP32 pipe (the pipe the taps need): the low
+// byte of the result is the same (values below 2^23).  Bit 0 = H pass, bit 1 = V pass.
+#ifndef GIP_FUSED_F2I
+#define GIP_FUSED_F2I 0
+#endif
+__device__ __forceinline__ uint32_t f2i_rz_bits(uint32_t fbits) {
+    uint32_t r;
+    asm("{.reg .f32 t; mov.b32 t, %1; cvt.rzi.u32.f32 %0, t;}" : "=r"(r) : "r"(fbits));
+    return r;
+}
+template <bool kXu>
+__device__ __forceinline__ uint64_t round_pair_sel(uint64_t acc) {
+    if (kXu) {
+        const uint64_t t = add_rn_x2(acc, splat_f2(0.5f));
+        return pack_f2(f2i_rz_bits(lo_f2(t)), f2i_rz_bits(hi_f2(t)));
+    }
+    return round_pair_f(acc);
 }
 
 // Shift a staged row left by a bytes (1..15), in place: logical chunk c = bytes [a, a + 16) of raw chunks c, c + 1.
@@ -344,13 +376,13 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                             rawA[4 * i] = a.x; rawA[4 * i + 1] = a.y; rawA[4 * i + 2] = a.z; rawA[4 * i + 3] = a.w;
                             rawB[4 * i] = b.x; rawB[4 * i + 1] = b.y; rawB[4 * i + 2] = b.z; rawB[4 * i + 3] = b.w;
                         }
-                        f[m] = pack_f2(byte_to_float_bits(rawA[bi >> 2], bi & 3), byte_to_float_bits(rawB[bi >> 2], bi & 3));
+                        f[m] = pack_f2(byte_to_float_bits_m<GIP_FUSED_XU_H>(rawA[bi >> 2], bi & 3), byte_to_float_bits_m<GIP_FUSED_XU_H>(rawB[bi >> 2], bi & 3));
                         const int j = m - 2 * RC;                // the output byte this input completes
                         if (j >= 0) {
                             uint64_t acc = mul_rn_x2(f[j], splat_f2(job.weights[0]));
 #pragma unroll
                             for (int t = 1; t < R2; t++) acc = fma_rn_x2(f[j + t * C], splat_f2(job.weights[t]), acc);
-                            const uint64_t z = round_pair_f(acc);
+                            const uint64_t z = round_pair_sel<(GIP_FUSED_F2I & 1) != 0>(acc);
                             zA[j & 3] = lo_f2(z); zB[j & 3] = hi_f2(z);
                             if ((j & 3) == 3) {
                                 wA[(j >> 2) & 3] = __byte_perm(__byte_perm(zA[0], zA[1], 0x4040), __byte_perm(zA[2], zA[3], 0x4040), 0x5410);
@@ -401,7 +433,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 const uint32_t ww[2] = {w.x, w.y};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint64_t v = pack_f2(byte_to_float_bits(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits(ww[q >> 1], 2 * (q & 1) + 1));
+                    const uint64_t v = pack_f2(byte_to_float_bits_m<GIP_FUSED_XU_V>(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits_m<GIP_FUSED_XU_V>(ww[q >> 1], 2 * (q & 1) + 1));
                     acc[q][u] = mul_rn_x2(v, splat_f2(job.weights[0]));
 #pragma unroll
                     for (int k = 1; k < R2; k++)
@@ -412,7 +444,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     uint32_t o[2];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const uint64_t z0 = round_pair_f(acc[2 * h][(u + 1) % R2]), z1 = round_pair_f(acc[2 * h + 1][(u + 1) % R2]);
+                        const uint64_t z0 = round_pair_sel<(GIP_FUSED_F2I & 2) != 0>(acc[2 * h][(u + 1) % R2]), z1 = round_pair_sel<(GIP_FUSED_F2I & 2) != 0>(acc[2 * h + 1][(u + 1) % R2]);
                         o[h] = __byte_perm(__byte_perm(lo_f2(z0), hi_f2(z0), 0x4040), __byte_perm(lo_f2(z1), hi_f2(z1), 0x4040), 0x5410);
                     }
                     if (kAny && tl.ret) {
