@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t byte_to_float_bits(uint32_t w, int b) {
 #define GIP_FUSED_XU_H 0
 #endif
 #ifndef GIP_FUSED_XU_V
-#define GIP_FUSED_XU_V 0
+#define GIP_FUSED_XU_V 15    // applied to the aligned kernel at R >= 3 only (see v_block)
 #endif
 template <int kMask>
 __device__ __forceinline__ uint32_t byte_to_float_bits_m(uint32_t w, int b) {
@@ -433,7 +433,11 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 const uint32_t ww[2] = {w.x, w.y};
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint64_t v = pack_f2(byte_to_float_bits_m<GIP_FUSED_XU_V>(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits_m<GIP_FUSED_XU_V>(ww[q >> 1], 2 * (q & 1) + 1));
+                    // Measured on B200 (c4 stream / 8K RGB): all V-pass conversions on the XU pipe 21.13 -> 20.60 ms, r = 4 109 -> 106 us,
+                    // but r = 1 71 -> 73 us and the any-alignment variant 33.6 -> 34.1 us; H-pass conversions there: no change
+                    // or slower; F2I for the truncation: 3-9 % slower.
+                    constexpr int kXuV = (!kAny && R >= 3) ? GIP_FUSED_XU_V : 0;
+                    const uint64_t v = pack_f2(byte_to_float_bits_m<kXuV>(ww[q >> 1], 2 * (q & 1)), byte_to_float_bits_m<kXuV>(ww[q >> 1], 2 * (q & 1) + 1));
                     acc[q][u] = mul_rn_x2(v, splat_f2(job.weights[0]));
 #pragma unroll
                     for (int k = 1; k < R2; k++)
