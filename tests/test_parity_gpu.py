@@ -502,6 +502,33 @@ def test_gaussian_wide_radii_fast_path(c, r, sigma):
     assert L.gip_launch_count() - before >= 2 * (6 + 1 + 4)
 
 
+@pytest.mark.parametrize("c,w", [(3, 239), (3, 241), (3, 243), (3, 481), (3, 721), (3, 7), (1, 239), (1, 241), (1, 483), (1, 1203), (1, 3)])
+@pytest.mark.parametrize("shift", [0, 1, 3])
+def test_sobel_any_alignment_strip_seams(c, w, shift):
+    """Sobel on rows at any byte alignment, widths on either side of the 240-pixel strip seams and narrower than one
+    lane: every strip -- the first and the last of a row included -- stages its row segments through the shared-memory
+    ring and stores through the slab (csrc/fast_sobel.cu, VB = 1); both levels against the oracle, canaries around the
+    output, a band height that is not a multiple of the 12-row tiles."""
+    import torch
+    from gpu_image_processing_b200 import device
+    h = 37
+    img = synth.uniform(h, w, c, seed=w * 3 + c + shift)
+    n = img.size
+    pad = 48
+    src = torch.zeros(n + 2 * pad, dtype=torch.uint8, device="cuda")
+    x = src[pad + shift: pad + shift + n].view(h, w, c)
+    x.copy_(torch.from_numpy(img))
+    for level in (1, 2):
+        dst = torch.full((n + 2 * pad,), 0x5A, dtype=torch.uint8, device="cuda")
+        lo = pad + (shift * 5) % 7
+        o = dst[lo: lo + n].view(h, w, c)
+        device.sobel_edge_detection(x, level, out=o)
+        torch.cuda.synchronize()
+        got = dst.cpu().numpy()
+        assert (got[:lo] == 0x5A).all() and (got[lo + n:] == 0x5A).all(), "wrote outside the output image"
+        _check("sobel", got[lo:lo + n].reshape(h, w, c), O.sobel(img, level), f"sobel seams level={level} shift={shift}")
+
+
 def test_c1_shape_odd_pitch_sobel_and_box():
     """The reference's README shape (3239 x 2146 RGB, 9717-byte rows: no row but the first is 4-byte aligned) through Sobel
     and box blur: fast path == general path on the whole image, oracle on the top rows, an interior band, the bottom rows."""
