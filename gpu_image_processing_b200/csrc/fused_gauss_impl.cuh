@@ -131,6 +131,9 @@ __device__ __forceinline__ uint64_t round_pair_f(uint64_t acc) {
 }
 // The truncation as two F2I on the XU pipe instead of one packed add on the FP32 pipe (the pipe the taps need): the low
 // byte of the result is the same (values below 2^23).  Bit 0 = H pass, bit 1 = V pass.
+#ifndef GIP_FUSED_H_SCATTER
+#define GIP_FUSED_H_SCATTER 1
+#endif
 #ifndef GIP_FUSED_F2I
 #define GIP_FUSED_F2I 0
 #endif
@@ -365,6 +368,9 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     const uint32_t ringB = ringA + kFRingPitch;
                     uint32_t rawA[4 * Cfg::kLaneChunks], rawB[4 * Cfg::kLaneChunks];
                     uint64_t f[kFLane + 2 * RC];                 // converted inputs (row A, row B); only 2RC+1 are live at a time
+#if GIP_FUSED_H_SCATTER
+                    uint64_t hacc[kFLane];                       // partial sums per output byte; only 2RC+1 are live at a time
+#endif
                     uint32_t zA[4], zB[4], wA[4], wB[4];
 #pragma unroll
                     for (int m = 0; m < kFLane + 2 * RC; m++) {
@@ -378,10 +384,24 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                         }
                         f[m] = pack_f2(byte_to_float_bits_m<GIP_FUSED_XU_H>(rawA[bi >> 2], bi & 3), byte_to_float_bits_m<GIP_FUSED_XU_H>(rawB[bi >> 2], bi & 3));
                         const int j = m - 2 * RC;                // the output byte this input completes
+#if GIP_FUSED_H_SCATTER
+                        // scatter form: input m is tap t of output m - t C -- 2R+1 independent FMAs per input instead of a chain
+                        // of 2R+1 dependent ones per output; every output still takes its taps in the reference's order
+#pragma unroll
+                        for (int t = 0; t < R2; t++) {
+                            const int jo = m - t * C;
+                            if (jo >= 0 && jo < kFLane)
+                                hacc[jo] = t == 0 ? mul_rn_x2(f[m], splat_f2(job.weights[0])) : fma_rn_x2(f[m], splat_f2(job.weights[t]), hacc[jo]);
+                        }
+#endif
                         if (j >= 0) {
+#if GIP_FUSED_H_SCATTER
+                            const uint64_t acc = hacc[j];
+#else
                             uint64_t acc = mul_rn_x2(f[j], splat_f2(job.weights[0]));
 #pragma unroll
                             for (int t = 1; t < R2; t++) acc = fma_rn_x2(f[j + t * C], splat_f2(job.weights[t]), acc);
+#endif
                             const uint64_t z = round_pair_sel<(GIP_FUSED_F2I & 1) != 0>(acc);
                             zA[j & 3] = lo_f2(z); zB[j & 3] = hi_f2(z);
                             if ((j & 3) == 3) {
