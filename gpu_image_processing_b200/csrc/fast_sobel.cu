@@ -83,6 +83,21 @@ __device__ __forceinline__ uint32_t biased_byte(const RowWords<C>& r, int idx) {
     return __byte_perm(r.w[idx >> 2], 0x4B000000u, 0x7540 | (idx & 3));
 }
 
+// Channel value of pixels (m, m + 4) as a float pair.  Default: PRMT into the mantissa of 2^23 and one packed add of -2^23
+// (ALU + FP32 pipe).  Channels in the mask GIP_SOBEL_XU_CH (bit 0 = R) convert with one I2F.U8 (byte selector) on the XU
+// pipe instead: no PRMT, no add, a quarter of the rate.
+#ifndef GIP_SOBEL_XU_CH
+#define GIP_SOBEL_XU_CH 0
+#endif
+template <int C>
+__device__ __forceinline__ uint64_t channel_pair(const RowWords<C>& r, int i0, int i1, int ch, uint64_t kNeg23) {
+    if ((GIP_SOBEL_XU_CH >> ch) & 1) {
+        const float a = (float)((r.w[i0 >> 2] >> (8 * (i0 & 3))) & 0xffu), b = (float)((r.w[i1 >> 2] >> (8 * (i1 & 3))) & 0xffu);
+        return pack_f2(__float_as_uint(a), __float_as_uint(b));
+    }
+    return add_rn_x2(pack_f2(biased_byte<C>(r, i0), biased_byte<C>(r, i1)), kNeg23);
+}
+
 template <int C, bool kU8>
 __device__ __forceinline__ GrayRow<kU8 || C == 1> make_gray(const RowWords<C>& r) {
     constexpr bool kInt = kU8 || C == 1;
@@ -94,9 +109,9 @@ __device__ __forceinline__ GrayRow<kU8 || C == 1> make_gray(const RowWords<C>& r
             Q[m] = add_rn_x2(pack_f2(biased_byte<C>(r, m), biased_byte<C>(r, m + 4)), kNeg23);
         } else {
             // pixel j: R = byte C*j, G = C*j+1, B = C*j+2
-            const uint64_t Rv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m), biased_byte<C>(r, C * (m + 4))), kNeg23);
-            const uint64_t Gv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m + 1), biased_byte<C>(r, C * (m + 4) + 1)), kNeg23);
-            const uint64_t Bv = add_rn_x2(pack_f2(biased_byte<C>(r, C * m + 2), biased_byte<C>(r, C * (m + 4) + 2)), kNeg23);
+            const uint64_t Rv = channel_pair<C>(r, C * m, C * (m + 4), 0, kNeg23);
+            const uint64_t Gv = channel_pair<C>(r, C * m + 1, C * (m + 4) + 1, 1, kNeg23);
+            const uint64_t Bv = channel_pair<C>(r, C * m + 2, C * (m + 4) + 2, 2, kNeg23);
             uint64_t g = fma_rn_x2(Bv, splat_f2(0.114f), fma_rn_x2(Rv, splat_f2(0.299f), mul_rn_x2(Gv, splat_f2(0.587f))));
             if (kU8)             // (float)(uchar)(gray + 0.5f): add, truncate on the 2^23 grid, remove the bias
                 g = add_rn_x2(add_rz_x2(add_rn_x2(g, splat_f2(0.5f)), splat_f2(8388608.0f)), kNeg23);

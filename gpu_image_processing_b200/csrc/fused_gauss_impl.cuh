@@ -50,7 +50,6 @@ constexpr int kFProd = 8, kFCons = 8;       // producer / consumer warps
 constexpr int kFThreads = 32 * (kFProd + kFCons);
 constexpr int kFStrip = 2048;               // output bytes per strip (32 lanes x 64 bytes)
 constexpr int kFLane = 64;
-constexpr int kFRingRows = 3 * kFK;         // the V pass consumes whole blocks of 2R+1 rows and may lag a step behind by up to 2R rows
 constexpr int kFRingPitch = kFStrip + kFStrip / 8;      // 2304: one pad chunk per 8 chunks
 
 // byte offset of byte `idx` of a row stored in the padded layout
@@ -78,7 +77,16 @@ template <int R, int C, bool kAny = false> struct FCfg {
     static constexpr int kStagePitch = 16 * (kRawChunks + (kRawChunks + 7) / 8);
     static constexpr int kLaneChunks = (kDelta + kFLane + 2 * RC + 15) / 16;   // chunks a lane reads per row
     static constexpr int kCopyIters = (kRawChunks + 31) / 32;
-    static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kFRingRows * kFRingPitch + kOutBytes;
+    // FIFO slots (steps of K rows).  The V pass consumes whole blocks of 2R+1 rows, so it may lag a step behind by up to 2R
+    // rows and the rows it takes per iteration vary (r = 3: 14, 14, 21, ...): three slots keep producers and consumers in
+    // lockstep (a producer's step p waits for the consumers' iteration p - 1), the fourth lets the producers run a step
+    // further ahead and absorbs that variation.  The any-alignment variant has no room for it (block of output rows).
+#ifndef GIP_FUSED_SLOTS
+#define GIP_FUSED_SLOTS 4
+#endif
+    static constexpr int kSlots = kAny ? 3 : GIP_FUSED_SLOTS;
+    static constexpr int kRingRows = kSlots * kFK;
+    static constexpr size_t kSmem = (size_t)2 * kFK * kStagePitch + (size_t)kRingRows * kFRingPitch + kOutBytes;
     static_assert(kSmem <= 227 * 1024, "shared memory");
     static_assert(kLaneChunks <= 8, "lane chunk addressing assumes at most 8 chunks");
 };
@@ -90,8 +98,9 @@ struct FusedTiling {
                         // 8-byte aligned (only the input needs the shift), the consumers store them themselves
 };
 
-// Named barriers 1..3 = FULL[slot], 4..6 = EMPTY[slot] (0 is __syncthreads).  Producers arrive on FULL[s % 3] when the rows
-// of step s are in the FIFO and consumers wait there; consumers arrive on EMPTY[s % 3] when every row of step s has been
+// Named barriers 1..NS = FULL[slot], NS+1..2NS = EMPTY[slot] (0 is __syncthreads; NS = 3 or 4 slots, the any-alignment
+// variant's consumer-only barriers 7 and 8 come after its 6).  Producers arrive on FULL[s % NS] when the rows
+// of step s are in the FIFO and consumers wait there; consumers arrive on EMPTY[s % NS] when every row of step s has been
 // consumed (end of their iteration s + 2: they take whole blocks of 2R+1 <= K+1 rows) and producers wait there before
 // step s + 3 overwrites the slot.  Every barrier counts all threads of the CTA (arrivals + waiters).
 __device__ __forceinline__ void fbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFThreads) : "memory"); }
@@ -187,7 +196,7 @@ template <int R, int C, bool kAny>
 __global__ void __launch_bounds__(kFThreads, 1)
 gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTiling tl) {
     using Cfg = FCfg<R, C, kAny>;
-    constexpr int RC = Cfg::RC, R2 = 2 * R + 1;
+    constexpr int RC = Cfg::RC, R2 = 2 * R + 1, NS = Cfg::kSlots;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t pitch = job.src.pitch;
@@ -207,7 +216,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
     const int64_t A0 = bxs - Cfg::kPad;              // image-row byte position of staged byte 0 (16-byte aligned)
     const uint32_t stage_s = smem_addr(smem);
     const uint32_t ring_s = stage_s + (uint32_t)(2 * kFK * Cfg::kStagePitch);
-    const uint32_t obuf_s = ring_s + (uint32_t)(kFRingRows * kFRingPitch);      // kAny: the block of output rows
+    const uint32_t obuf_s = ring_s + (uint32_t)(Cfg::kRingRows * kFRingPitch);      // kAny: the block of output rows
 
     if (warp < kFProd) {
         // ==================================== producer warp: rows 2*warp, 2*warp + 1 of every step ====================
@@ -361,10 +370,10 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                     }
                     __syncwarp();
                 }
-                if (tl.decoupled && step >= 3) fbar_sync(4 + step % 3);      // the consumers are done with step - 3 (same slot)
+                if (tl.decoupled && step >= NS) fbar_sync(NS + 1 + step % NS);      // the consumers are done with step - NS (same slot)
                 if (rel < nrows_in) {
                     // ---- H pass of rows rel (low halves of every pair) and rel + 1 (high halves)
-                    const uint32_t ringA = ring_s + (uint32_t)(((step % 3) * kFK + 2 * warp) * kFRingPitch + lane_base);
+                    const uint32_t ringA = ring_s + (uint32_t)(((step % NS) * kFK + 2 * warp) * kFRingPitch + lane_base);
                     const uint32_t ringB = ringA + kFRingPitch;
                     uint32_t rawA[4 * Cfg::kLaneChunks], rawB[4 * Cfg::kLaneChunks];
                     uint64_t f[kFLane + 2 * RC];                 // converted inputs (row A, row B); only 2RC+1 are live at a time
@@ -418,7 +427,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 __syncwarp();                        // every lane has read this buffer: refill it for step + 2
                 stage_rows(step + 2);
             }
-            if (tl.decoupled) fbar_arrive(1 + step % 3);
+            if (tl.decoupled) fbar_arrive(1 + step % NS);
             else __syncthreads();
         }
     } else {
@@ -441,7 +450,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         for (int q = 0; q < 4; q++)
 #pragma unroll
             for (int t = 0; t < R2; t++) acc[q][t] = 0;
-        const uint32_t ring_end = ring_tid + (uint32_t)(kFRingRows * kFRingPitch);
+        const uint32_t ring_end = ring_tid + (uint32_t)(Cfg::kRingRows * kFRingPitch);
         uint32_t a = ring_tid;                       // FIFO row of input row `done`
         int done = 0;                                // input rows consumed so far (a multiple of 2R+1)
         auto v_block = [&](auto steady_tag) {
@@ -485,7 +494,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
         for (int step = 0; step <= nsteps; step++) {
             if (tl.decoupled) {
                 if (step == 0) continue;
-                fbar_sync(1 + (step - 1) % 3);       // the rows of step - 1 are in the FIFO
+                fbar_sync(1 + (step - 1) % NS);      // the rows of step - 1 are in the FIFO
             }
             if (kAny && tl.ret) o_s = obuf_s + 8u * (uint32_t)vt;
             if (any) {
@@ -518,7 +527,7 @@ gip_gauss_fused(const __grid_constant__ Job job, const __grid_constant__ FusedTi
                 asm volatile("bar.sync 8, %0;" ::"n"(32 * kFCons) : "memory");
             }
             if (!tl.decoupled) __syncthreads();
-            else if (step >= 2 && step + 1 <= nsteps - 1) fbar_arrive(4 + (step - 2) % 3);   // a producer waits for it at step + 1
+            else if (step >= 2 && step + NS - 2 <= nsteps - 1) fbar_arrive(NS + 1 + (step - 2) % NS);   // every row of step - 2 is consumed; a producer waits for it at step + NS - 2
         }
     }
 }
