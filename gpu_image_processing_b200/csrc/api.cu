@@ -257,7 +257,10 @@ static cudaError_t run_sync(FilterKind kind, const uint8_t* d_in, uint8_t* d_out
 }
 
 // ---- host-buffer path: cached pinned + device staging ---------------------------------------
-constexpr int kMaxChunks = 32;
+#ifndef GIP_MAX_CHUNKS
+#define GIP_MAX_CHUNKS 32
+#endif
+constexpr int kMaxChunks = GIP_MAX_CHUNKS;
 
 static long env_long(const char* name, long fallback) {
     const char* e = getenv(name);
