@@ -24,6 +24,10 @@
 // The edge value is replicated into every channel, alpha included (:1311-1313).
 // Warps whose 32 lanes all lie inside the row (every strip but the first and the last one or two of a
 // row) run a path without per-word offsets, masks and store predicates.
+// Rows at any byte alignment (VB = 1: odd pitches, unaligned base pointers) keep this kernel and this stencil code; a
+// warp's row segments come in through a per-warp shared-memory ring filled with 16-byte cp.async from the aligned global
+// chunks that cover them, and its output rows leave through a per-warp slab and whole 16-byte stores at the aligned
+// global addresses (see ring_mem / oslab_mem in the kernel).
 #include <atomic>
 #include <cstdlib>
 #include <type_traits>

@@ -12,8 +12,9 @@
 //                      (FFMA2), so one issue slot does two taps and nothing is ever re-packed.  Lane l owns 64 output
 //                      bytes of both rows: it reads its 64 + 2*R*C input bytes with LDS.128, converts each byte once
 //                      (PRMT + I2FP, off the FP32 pipe) and accumulates every output in the reference's tap order
-//                      (:86-99: i = -R..R, one FMA per tap, first tap a multiply), rounds (:102) and writes the row
-//                      into the FIFO with STS.128.
+//                      (:86-99: i = -R..R, one FMA per tap, first tap a multiply; scatter form: an input is tap t of
+//                      output m - tC, so the 2R+1 FMAs it feeds are independent), rounds (:102) and writes the row
+//                      into the FIFO (four steps of K rows; three in the any-alignment variant) with STS.128.
 //   8 consumer warps   run the V pass one step behind.  A thread owns an 8-byte column group and keeps the 2R+1
 //                      partial sums of its columns in registers: a new FIFO row v updates  acc[t] = fma(v, w[t], acc[t-1])
 //                      for t = 2R..1, acc[0] = v * w[0]  (the rotation of the accumulators happens in the FMA's
